@@ -1,0 +1,25 @@
+# Builds the C-ABI shared library (sm_100a only) and the oracle's C helpers.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
+             --expt-relaxed-constexpr
+CSRC      := videopose3d_b200/csrc
+LIBDIR    := videopose3d_b200/_lib
+LIB       := $(LIBDIR)/libvp3d_b200.so
+SRCS      := $(CSRC)/conv_gemm.cu $(CSRC)/pack.cu $(CSRC)/api.cu
+OBJS      := $(SRCS:$(CSRC)/%.cu=$(LIBDIR)/%.o)
+HDRS      := $(wildcard $(CSRC)/*.cuh) include/vp3d_b200.h
+
+all: $(LIB)
+
+$(LIBDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker --exclude-libs=ALL
+
+clean:
+	rm -rf $(LIBDIR)
+
+.PHONY: all clean

@@ -1,0 +1,168 @@
+/*
+ * vp3d_b200 — C ABI of the B200-native temporal-convolution engine that replaces the
+ * PyTorch/cuDNN execution of VideoPose3D's model hot path.
+ *
+ * The reference (facebookresearch/VideoPose3D) has no FFI: its "operator interface" for this path
+ * is the nn.Module contract of common/model.py (TemporalModelBase :10-77, TemporalModel :79-138,
+ * TemporalModelOptimized1f :140-197) as exercised by run.py.  Each entry point below names the
+ * reference call site it replaces.  All pointers are plain host/device addresses, sizes are plain
+ * integers, streams are cudaStream_t passed as void*; nothing here depends on torch.
+ *
+ * Conventions: every function returns 0 on success or a negative vp3d_status; the message for the
+ * last failure on the calling thread is available from vp3d_last_error().  The library never
+ * aborts the process and never falls back to a CPU path.
+ */
+#ifndef VP3D_B200_H_
+#define VP3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP3D_VERSION 100
+#define VP3D_MAX_WIDTHS 8                       /* len(filter_widths) <= 8 (RF up to 3^8) */
+#define VP3D_MAX_LAYERS (2 * (VP3D_MAX_WIDTHS - 1)) /* layers_conv / layers_bn entries */
+
+typedef enum {
+  VP3D_OK = 0,
+  VP3D_ERR_INVALID = -1,     /* bad argument (mirrors the AssertionErrors of model.py:20-21, 64-66) */
+  VP3D_ERR_UNSUPPORTED = -2, /* configuration the kernels do not cover; never a silent fallback */
+  VP3D_ERR_CUDA = -3,        /* CUDA runtime / driver error, text in vp3d_last_error() */
+  VP3D_ERR_WORKSPACE = -4,   /* workspace too small / misaligned */
+  VP3D_ERR_STATE = -5        /* call order violated (e.g. forward before weights were loaded) */
+} vp3d_status;
+
+typedef enum {
+  VP3D_VARIANT_DILATED = 0,  /* TemporalModel            (model.py:79-138)  */
+  VP3D_VARIANT_STRIDED = 1   /* TemporalModelOptimized1f (model.py:140-197) */
+} vp3d_variant;
+
+typedef enum {
+  VP3D_PRECISION_BF16 = 0,   /* bf16 operands, fp32 accumulate (fast path; BASELINE cfg 2) */
+  VP3D_PRECISION_BF16X3 = 1  /* split-bf16 (hi+lo) operands, 3 MMAs per product: fp32-faithful */
+} vp3d_precision;
+
+/* Constructor arguments of TemporalModel / TemporalModelOptimized1f (model.py:85-86, :151-152). */
+typedef struct {
+  int num_joints_in;
+  int in_features;
+  int num_joints_out;
+  int num_widths;
+  int filter_widths[VP3D_MAX_WIDTHS];
+  int causal;
+  int channels;
+  int dense;      /* TemporalModel(dense=True) ablation, model.py:113-116 */
+  int variant;    /* vp3d_variant */
+  int precision;  /* vp3d_precision */
+} vp3d_config;
+
+/* Device pointers to the fp32 tensors of the module's state_dict (same names / shapes as the
+ * reference: expand_conv.weight (C, J*F, w0); expand_bn.{weight,bias,running_mean,running_var};
+ * layers_conv.{i}.weight; layers_bn.{i}.*; shrink.weight (3*J_out, C, 1); shrink.bias). */
+typedef struct {
+  const float* expand_conv_weight;
+  const float* expand_bn[4]; /* weight, bias, running_mean, running_var */
+  const float* layers_conv_weight[VP3D_MAX_LAYERS];
+  const float* layers_bn[VP3D_MAX_LAYERS][4];
+  const float* shrink_weight;
+  const float* shrink_bias;
+} vp3d_weights;
+
+typedef struct vp3d_plan vp3d_plan;
+
+int vp3d_version(void);
+const char* vp3d_last_error(void);
+
+/* Replaces TemporalModel.__init__ / TemporalModelOptimized1f.__init__ (model.py:85-124, 151-185):
+ * validates odd filter widths, derives pad / causal_shift / dilation per block, allocates the packed
+ * bf16 weight store on the current CUDA device. */
+int vp3d_plan_create(const vp3d_config* cfg, vp3d_plan** out_plan);
+void vp3d_plan_destroy(vp3d_plan* plan);
+
+/* Replaces TemporalModelBase.receptive_field (model.py:41-48). */
+int vp3d_receptive_field(const vp3d_plan* plan);
+/* Replaces TemporalModelBase.total_causal_shift (model.py:50-61). */
+int vp3d_total_causal_shift(const vp3d_plan* plan);
+
+/* Re-pack parameters after load_state_dict / optimizer.step (state_dict contract, run.py:209-210,
+ * 426).  what: bit 0 = conv weights -> bf16 planes, bit 1 = BatchNorm eval affine
+ * (scale = w / sqrt(running_var + 1e-5), shift = b - running_mean * scale) and shrink bias. */
+#define VP3D_PACK_CONV 1
+#define VP3D_PACK_BN_EVAL 2
+int vp3d_set_weights(vp3d_plan* plan, const vp3d_weights* w, int what, void* stream);
+
+/* Output frames for an input of T frames: T - receptive_field + 1 for the dilated variant
+ * (model.py:130-135 valid convolutions), floor-division chain for the strided one (:167, :178). */
+int vp3d_output_frames(const vp3d_plan* plan, int T);
+
+/* Bytes of device scratch needed by vp3d_forward_eval for a batch of N sequences of T frames. */
+size_t vp3d_workspace_bytes(const vp3d_plan* plan, int N, int T);
+
+/* Replaces TemporalModelBase.forward in eval() mode (model.py:63-77 + _forward_blocks :126-138 /
+ * :187-197): x is (N, T, J_in, F) fp32 contiguous, y is (N, T_out, J_out, 3) fp32 contiguous, both
+ * DEVICE pointers.  workspace is device memory of at least vp3d_workspace_bytes(), 1024-B aligned.
+ * Asynchronous on `stream`. */
+int vp3d_forward_eval(vp3d_plan* plan, const float* x, float* y, int N, int T, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Same computation with HOST buffers (the call run.py makes: numpy batch -> .cuda() -> model ->
+ * .cpu(), run.py:663-672): copies x host->device, runs the forward, copies y device->host and
+ * synchronises.  Device staging buffers are owned by the plan.  x_host / y_host should be pinned
+ * for full PCIe bandwidth but pageable memory is accepted. */
+int vp3d_forward_eval_host(vp3d_plan* plan, const float* x_host, float* y_host, int N, int T);
+
+/* Number of kernels the last forward on this plan launched (for bench.py's gpu_launches). */
+int vp3d_last_launch_count(const vp3d_plan* plan);
+
+/* ---- operator-level entry (used by the parity tests; the model-level calls are built on it) ----
+ * One temporal convolution on channel-last bf16 activations with the fused epilogue.
+ * Replaces nn.Conv1d (+ BatchNorm1d eval affine + ReLU + residual slice-add), model.py:127, 134-135. */
+typedef struct {
+  /* A operand: bf16, [a_planes][samples][a_rows][a_ld] (a_ld = elements per row, multiple of 64) */
+  const void* a;
+  int a_planes;
+  int samples;
+  int a_rows;
+  int a_ld;
+  /* W operand: bf16, [w_planes][taps][n_pad][k_per_tap] */
+  const void* w;
+  int taps;
+  int k_per_tap; /* multiple of 64 */
+  int n_pad;     /* multiple of 64 */
+  /* geometry */
+  int per_sample_tiles; /* 1: tile = 128 output rows of one sample; 0: rows flattened over samples */
+  int tap_row_step;     /* input-row offset between taps (dilation), 0 when taps are column blocks */
+  int tap_col_step;     /* input-column offset between taps (strided conv: k_per_tap), else 0 */
+  int out_rows;         /* output rows per sample (per_sample_tiles) or in total (flat) */
+  int precision;        /* vp3d_precision */
+  /* epilogue */
+  const float* scale;   /* per channel, may be NULL (-> no affine) */
+  const float* shift;
+  int relu;
+  const void* res;      /* bf16 residual [res_planes][*][res_ld] or NULL */
+  int res_planes;
+  long long res_plane_stride; /* elements */
+  int res_ld;
+  int res_rows_per_sample;
+  int res_row_step;
+  int res_row_off;
+  int res_sample_div;   /* flat tiling only: rows per sample used to split row -> (sample, t); 0 = none */
+  void* out;            /* bf16 [out_planes][rows][out_ld] or NULL */
+  int out_planes;
+  long long out_plane_stride; /* elements */
+  int out_ld;
+  float* out_f32;       /* fp32 [rows][out_f32_ld] (first n_valid channels) or NULL */
+  int out_f32_ld;
+  int n_valid;
+  float* stats;         /* [2][n_pad] sum / sum-of-squares accumulators or NULL */
+} vp3d_conv_desc;
+
+int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP3D_B200_H_ */

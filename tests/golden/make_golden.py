@@ -1,0 +1,118 @@
+"""Generate golden vectors from the REAL reference implementation.
+
+Run in the build container only (needs /root/reference, which does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+Imports ``common.model`` from /root/reference unchanged, loads seeded parameters into the reference
+classes, runs them on CPU in float32 and stores inputs / parameters / outputs as small ``.npz``
+fixtures next to this script.  The oracle (oracle/temporal_model_oracle.py) and the CUDA path are
+both checked against these files (tests/test_oracle_golden.py, tests/test_gpu_parity.py).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from common.model import TemporalModel, TemporalModelOptimized1f  # noqa: E402  (the reference)
+
+from oracle import temporal_model_oracle as orc  # noqa: E402
+
+# name -> config.  "store_sd": parameters are written into the fixture (small models); otherwise
+# they are regenerated from `seed` with oracle.make_state_dict (large models).
+CASES = {
+    "tm_333_c64": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=3, T=33),
+    "tm_333_c64_causal": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=2, T=40,
+                              causal=True),
+    "tm_33_c64_dense": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3], C=64, N=2, T=12,
+                            dense=True),
+    "tm_353_c128_traj": dict(cls="TemporalModel", J=16, F=3, Jout=1, fw=[3, 5, 3], C=128, N=2, T=50),
+    "tm_333_c64_rf": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=5, T=27),
+    "tm_333_c64_rf_causal": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=5,
+                                 T=27, causal=True),
+    "opt_333_c64": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=5,
+                        T=27),
+    "opt_333_c64_causal": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64,
+                               N=5, T=27, causal=True),
+    "opt_35_c64": dict(cls="TemporalModelOptimized1f", J=15, F=2, Jout=15, fw=[3, 5], C=64, N=130,
+                       T=15),
+    "tm_3_c64": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3], C=64, N=2, T=9),
+    "tm_333_c64_train": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=4, T=30,
+                             train=True, momentum=0.07),
+    "opt_333_c64_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64,
+                              N=6, T=27, train=True, momentum=0.1),
+    # BASELINE configs[0]: arc 3,3,3, 17 joints, N=64, CPU fp32 forward (C = 1024)
+    "cfg1_tm_333_c1024": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=1024, N=64,
+                              T=27, store_sd=False),
+    "tm_333_c1024_long": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=1024, N=2,
+                              T=300, store_sd=False),
+    # BASELINE configs[1] shape (arc 3^5, T = 243) at a batch the CPU reference finishes in seconds
+    "cfg2_tm_33333_c1024": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3, 3, 3], C=1024,
+                                N=8, T=243, store_sd=False),
+    "tm_33333_c1024_t250": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3, 3, 3], C=1024,
+                                N=2, T=250, store_sd=False),
+    "opt_33333_c1024": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3, 3, 3],
+                            C=1024, N=8, T=243, store_sd=False),
+}
+
+
+def build_case(name, cfg):
+    seed = abs(hash(name)) % 1000 if False else sum(ord(c) for c in name)  # stable across runs
+    causal = bool(cfg.get("causal", False))
+    dense = bool(cfg.get("dense", False))
+    sd = orc.make_state_dict(cfg["J"], cfg["F"], cfg["Jout"], cfg["fw"], cfg["C"], dense=dense,
+                             seed=seed)
+    x = orc.make_input(cfg["N"], cfg["T"], cfg["J"], cfg["F"], seed=seed + 1)
+    kw = dict(filter_widths=cfg["fw"], causal=causal, dropout=0.0, channels=cfg["C"])
+    if cfg["cls"] == "TemporalModel":
+        model = TemporalModel(cfg["J"], cfg["F"], cfg["Jout"], dense=dense, **kw)
+    else:
+        model = TemporalModelOptimized1f(cfg["J"], cfg["F"], cfg["Jout"], **kw)
+    model.load_state_dict(sd)
+    out = {}
+    if cfg.get("train"):
+        model.train()
+        model.set_bn_momentum(cfg["momentum"])
+        y = model(x).detach()
+        new_sd = model.state_dict()
+        for k, v in new_sd.items():
+            if "running" in k or "num_batches" in k:
+                out["new/" + k] = v.numpy()
+    else:
+        model.eval()
+        with torch.no_grad():
+            y = model(x)
+    meta = dict(cfg)
+    meta.update(name=name, seed=seed, causal=causal, dense=dense,
+                receptive_field=model.receptive_field(), torch=torch.__version__,
+                reference_commit="1afb1ca0f1237776518469876342fc8669d3f6a9")
+    out["meta"] = np.array(json.dumps(meta))
+    out["y"] = y.numpy()
+    if cfg.get("store_sd", True):
+        out["x"] = x.numpy()
+        for k, v in sd.items():
+            out["sd/" + k] = v.numpy()
+    return out
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
+    for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
+        data = build_case(name, cfg)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: y{tuple(data['y'].shape)} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""CPU: pin the oracle (both restatements) against the golden vectors produced by the real
+reference (tests/golden/make_golden.py).  Tolerances: the NumPy float64 restatement must agree with
+the reference's float32 CPU output to float32 round-off (<= 2e-5 of the output scale); the
+torch.nn.functional restatement (float32) likewise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import temporal_model_oracle as orc
+
+SMALL = [n for n in golden_names() if "c1024" not in n]
+LARGE = [n for n in golden_names() if "c1024" in n]
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.mark.parametrize("name", SMALL + LARGE)
+def test_numpy_restatement_matches_reference(name):
+    meta, sd, x, y_ref, new = load_golden(name)
+    if meta["C"] == 1024 and meta["N"] * meta["T"] > 2000:
+        x, y_ref = x[:2], y_ref[:2]  # keep the CPU suite fast; batch rows are independent in eval
+    strided = meta["cls"] == "TemporalModelOptimized1f"
+    train = bool(meta.get("train"))
+    res = orc.forward_numpy(sd, x.numpy(), meta["fw"], causal=meta["causal"], dense=meta["dense"],
+                            strided=strided, training=train, momentum=meta.get("momentum", 0.1),
+                            return_new_stats=train)
+    y = res[0] if train else res
+    assert y.shape == y_ref.shape
+    assert _rel(y, y_ref) < 2e-5
+    if train:
+        for k, v in new.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(res[1][k]) == int(v)
+            else:
+                assert _rel(res[1][k], v) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", SMALL + LARGE)
+def test_torch_restatement_matches_reference(name):
+    meta, sd, x, y_ref, new = load_golden(name)
+    if meta["C"] == 1024 and meta["N"] * meta["T"] > 2000:
+        x, y_ref = x[:2], y_ref[:2]
+    strided = meta["cls"] == "TemporalModelOptimized1f"
+    train = bool(meta.get("train"))
+    sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        y = orc.forward_torch(sd, x, meta["fw"], causal=meta["causal"], dense=meta["dense"],
+                              strided=strided, training=train, momentum=meta.get("momentum", 0.1),
+                              update_stats=train)
+    assert tuple(y.shape) == y_ref.shape
+    assert _rel(y.numpy(), y_ref) < 2e-5
+    if train:
+        for k, v in new.items():
+            if not k.endswith("num_batches_tracked"):
+                assert _rel(sd[k].numpy(), v) < 2e-5, k
+
+
+def test_eval_cone_equals_dilated():
+    """The property the strided eval schedule relies on: with running statistics,
+    TemporalModel on one receptive field == TemporalModelOptimized1f, causal or not."""
+    for name in ("tm_333_c64_rf", "tm_333_c64_rf_causal"):
+        meta, sd, x, y_ref, _ = load_golden(name)
+        y = orc.forward_numpy(sd, x.numpy(), meta["fw"], causal=meta["causal"], strided=True)
+        assert _rel(y, y_ref) < 2e-5
+
+
+def test_arch_bookkeeping():
+    a = orc.arch([3, 3, 3, 3, 3])
+    assert a["receptive_field"] == 243 and a["pad"] == [1, 3, 9, 27, 81]
+    assert orc.arch([3, 3, 3], causal=True)["shift"] == [1, 3, 9]
+    assert orc.arch([3, 3, 3], causal=True, strided=True)["shift"] == [1, 1, 1]
+    with pytest.raises(AssertionError):
+        orc.arch([3, 4])

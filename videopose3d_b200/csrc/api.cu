@@ -1,0 +1,621 @@
+// C-ABI implementation: plan construction, parameter packing, eval-mode forward schedules
+// (strided / dependency-cone and dilated) built from the conv GEMM kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vp3d_b200.h"
+#include "conv_gemm.cuh"
+#include "pack.cuh"
+
+using namespace vp3d;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(VP3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+#define VP3D_TRY(expr)          \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != VP3D_OK) return _s; \
+  } while (0)
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D bf16 map (k, row, sample, plane), box (64, box_rows, 1, 1), 128-byte swizzle.
+static int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+                       uint64_t row_stride, uint64_t samples, uint64_t sample_stride,
+                       uint64_t planes, uint64_t plane_stride, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride * 2) % 16 || (sample_stride * 2) % 16 ||
+      (plane_stride * 2) % 16)
+    return fail(VP3D_ERR_INVALID, "tensor map operand not 16-byte aligned");
+  cuuint64_t dims[4] = {inner, rows, samples, planes};
+  cuuint64_t strides[3] = {row_stride * 2, sample_stride * 2, plane_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VP3D_ERR_CUDA,
+                "cuTensorMapEncodeTiled(4d) failed: %d (inner=%llu rows=%llu rs=%llu samples=%llu "
+                "ss=%llu planes=%llu ps=%llu)",
+                (int)r, (unsigned long long)inner, (unsigned long long)rows,
+                (unsigned long long)row_stride, (unsigned long long)samples,
+                (unsigned long long)sample_stride, (unsigned long long)planes,
+                (unsigned long long)plane_stride);
+  return VP3D_OK;
+}
+
+// 2-D bf16 map (k, row), box (64, box_rows), 128-byte swizzle.
+static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+                       uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (inner=%llu rows=%llu)",
+                (int)r, (unsigned long long)inner, (unsigned long long)rows);
+  return VP3D_OK;
+}
+
+static int pick_block_n(int n_pad) {
+  if (n_pad % 256 == 0) return 256;
+  if (n_pad % 128 == 0) return 128;
+  return 64;
+}
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ------------------------------------------------------------------ operator level
+static int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
+  if (!d || !d->a || !d->w) return fail(VP3D_ERR_INVALID, "conv_gemm: null operand");
+  if (d->a_ld % 64 || d->k_per_tap % 64 || d->n_pad % 64)
+    return fail(VP3D_ERR_INVALID, "conv_gemm: a_ld, k_per_tap and n_pad must be multiples of 64");
+  if (d->taps < 1 || d->out_rows < 0 || d->samples < 1)
+    return fail(VP3D_ERR_INVALID, "conv_gemm: bad geometry");
+  if (d->out_rows == 0) return VP3D_OK;
+  const int a_planes = d->a_planes > 0 ? d->a_planes : 1;
+  const int pairs = d->precision == VP3D_PRECISION_BF16X3 ? 3 : 1;
+  if (pairs == 3 && a_planes != 2)
+    return fail(VP3D_ERR_INVALID, "conv_gemm: bf16x3 needs hi/lo planes of A");
+  const int w_planes = pairs == 3 ? 2 : 1;
+  const int block_n = pick_block_n(d->n_pad);
+
+  CUtensorMap ma, mw;
+  const uint64_t a_rows = d->a_rows, a_ld = d->a_ld;
+  const uint64_t plane_stride = (uint64_t)d->samples * a_rows * a_ld;
+  VP3D_TRY(make_map_4d(&ma, d->a, a_ld, a_rows, a_ld, d->samples, a_rows * a_ld, a_planes,
+                       plane_stride, kBlockM));
+  VP3D_TRY(make_map_2d(&mw, d->w, d->k_per_tap, (uint64_t)w_planes * d->taps * d->n_pad, block_n));
+
+  ConvGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.dilated = d->per_sample_tiles ? 1 : 0;
+  g.samples = d->samples;
+  g.out_rows = d->out_rows;
+  g.tiles_per_sample = (d->out_rows + kBlockM - 1) / kBlockM;
+  g.taps = d->taps;
+  g.kblocks_per_tap = d->k_per_tap / kBlockK;
+  g.tap_row_step = d->tap_row_step;
+  g.tap_col_step = d->tap_col_step;
+  g.n_pad = d->n_pad;
+  g.n_tiles = d->n_pad / block_n;
+  g.pairs = pairs;
+  g.flags = 0;
+  if (d->scale && d->shift) g.flags |= kEpiAffine;
+  if (d->relu) g.flags |= kEpiRelu;
+  if (d->res) g.flags |= kEpiResidual;
+  if (d->stats) g.flags |= kEpiStats;
+  if (d->out_f32) g.flags |= kEpiOutF32;
+  g.scale = d->scale;
+  g.shift = d->shift;
+  g.res = static_cast<const __nv_bfloat16*>(d->res);
+  g.res_plane_stride = d->res_plane_stride;
+  g.res_planes = d->res ? (d->res_planes > 0 ? d->res_planes : 1) : 0;
+  g.res_ld = d->res_ld;
+  g.res_rows_per_sample = d->res_rows_per_sample;
+  g.res_row_step = d->res_row_step;
+  g.res_row_off = d->res_row_off;
+  g.res_sample_div = d->res_sample_div;
+  g.out = static_cast<__nv_bfloat16*>(d->out);
+  g.out_plane_stride = d->out_plane_stride;
+  g.out_planes = d->out_planes > 0 ? d->out_planes : 1;
+  g.out_ld = d->out_ld;
+  g.out_f32 = d->out_f32;
+  g.out_f32_ld = d->out_f32_ld;
+  g.n_valid = d->n_valid > 0 ? d->n_valid : d->n_pad;
+  g.stats = d->stats;
+  if (!d->out && !d->out_f32) return fail(VP3D_ERR_INVALID, "conv_gemm: no output");
+  if (d->out && (d->out_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: out_ld % 8 != 0");
+  if (d->res && (d->res_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: res_ld % 8 != 0");
+  CUDA_TRY(launch_conv_gemm(ma, mw, g, block_n, num_sms(), stream));
+  return VP3D_OK;
+}
+
+// ------------------------------------------------------------------ plan
+struct PackedConv {
+  __nv_bfloat16* w = nullptr;
+  int taps = 0;       // taps as stored (1 when merged)
+  int k_per_tap = 0;  // padded
+  int n_pad = 0;
+  int merged = 0;
+  float* scale = nullptr;  // eval affine [n_pad]
+  float* shift = nullptr;
+};
+
+struct vp3d_plan {
+  vp3d_config cfg;
+  int nb = 0;  // residual blocks
+  int C = 0, c_in_raw = 0, c_out_raw = 0, c_in_pad = 0, k0_pad = 0, c_out_pad = 0;
+  int planes = 1;
+  int pad[VP3D_MAX_WIDTHS];
+  int shift_dil[VP3D_MAX_WIDTHS];  // causal shift in frames (TemporalModel, model.py:111)
+  int shift_str[VP3D_MAX_WIDTHS];  // causal shift in strided units (Optimized1f, model.py:176)
+  int dilation[VP3D_MAX_WIDTHS];
+  int taps[VP3D_MAX_WIDTHS];       // taps of block i's first conv (dense: 2*pad+1)
+  PackedConv expand_dil, expand_flat, shrink;
+  PackedConv conv[VP3D_MAX_LAYERS];
+  std::vector<void*> allocs;
+  bool conv_packed = false, bn_packed = false;
+  // host-API staging (owned)
+  float* d_x = nullptr;
+  float* d_y = nullptr;
+  void* d_ws = nullptr;
+  size_t d_x_bytes = 0, d_y_bytes = 0, d_ws_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int last_launches = 0;
+};
+
+static int plan_alloc(vp3d_plan* p, void** out, size_t bytes) {
+  void* q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, bytes));
+  p->allocs.push_back(q);
+  *out = q;
+  return VP3D_OK;
+}
+
+static int alloc_packed(vp3d_plan* p, PackedConv& pc, int taps, int k_per_tap, int n_pad,
+                        int merged) {
+  pc.taps = taps;
+  pc.k_per_tap = k_per_tap;
+  pc.n_pad = n_pad;
+  pc.merged = merged;
+  const size_t elems = (size_t)p->planes * taps * n_pad * k_per_tap;
+  VP3D_TRY(plan_alloc(p, reinterpret_cast<void**>(&pc.w), elems * 2));
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_version(void) { return VP3D_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char* vp3d_last_error(void) { return g_err; }
+
+extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3d_config* cfg, vp3d_plan** out_plan) {
+  if (!cfg || !out_plan) return fail(VP3D_ERR_INVALID, "plan_create: null argument");
+  if (cfg->num_widths < 1 || cfg->num_widths > VP3D_MAX_WIDTHS)
+    return fail(VP3D_ERR_INVALID, "plan_create: len(filter_widths) must be in [1, %d]",
+                VP3D_MAX_WIDTHS);
+  for (int i = 0; i < cfg->num_widths; ++i)
+    if (cfg->filter_widths[i] < 1 || cfg->filter_widths[i] % 2 == 0)
+      return fail(VP3D_ERR_INVALID, "Only odd filter widths are supported");  // model.py:20-21
+  if (cfg->num_joints_in < 1 || cfg->in_features < 1 || cfg->num_joints_out < 1)
+    return fail(VP3D_ERR_INVALID, "plan_create: joint / feature counts must be positive");
+  if (cfg->channels < 64 || cfg->channels % 64)
+    return fail(VP3D_ERR_UNSUPPORTED, "channels must be a positive multiple of 64 (got %d)",
+                cfg->channels);
+  if (cfg->variant != VP3D_VARIANT_DILATED && cfg->variant != VP3D_VARIANT_STRIDED)
+    return fail(VP3D_ERR_INVALID, "plan_create: unknown variant %d", cfg->variant);
+  if (cfg->variant == VP3D_VARIANT_STRIDED && cfg->dense)
+    return fail(VP3D_ERR_INVALID, "dense=True only exists for TemporalModel");
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaFree(0) != cudaSuccess)
+    return fail(VP3D_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+
+  vp3d_plan* p = new vp3d_plan();
+  p->cfg = *cfg;
+  p->nb = cfg->num_widths - 1;
+  p->C = cfg->channels;
+  p->c_in_raw = cfg->num_joints_in * cfg->in_features;
+  p->c_out_raw = cfg->num_joints_out * 3;
+  p->c_in_pad = round_up(p->c_in_raw, 64);
+  p->k0_pad = round_up(p->c_in_raw * cfg->filter_widths[0], 64);
+  p->c_out_pad = round_up(p->c_out_raw, 64);
+  p->planes = cfg->precision == VP3D_PRECISION_BF16X3 ? 2 : 1;
+  // model.py:31, 107-121 / :172-184
+  p->pad[0] = cfg->filter_widths[0] / 2;
+  p->shift_dil[0] = p->shift_str[0] = cfg->causal ? cfg->filter_widths[0] / 2 : 0;
+  p->dilation[0] = 1;
+  p->taps[0] = cfg->filter_widths[0];
+  int next_dilation = cfg->filter_widths[0];
+  for (int i = 1; i < cfg->num_widths; ++i) {
+    const int w = cfg->filter_widths[i];
+    p->pad[i] = (w - 1) * next_dilation / 2;
+    p->shift_dil[i] = cfg->causal ? (w / 2) * next_dilation : 0;
+    p->shift_str[i] = cfg->causal ? (w / 2) : 0;
+    p->dilation[i] = cfg->dense ? 1 : next_dilation;
+    p->taps[i] = cfg->dense ? 2 * p->pad[i] + 1 : w;
+    next_dilation *= w;
+  }
+
+  int st = VP3D_OK;
+  do {
+    if ((st = alloc_packed(p, p->expand_dil, cfg->filter_widths[0], p->c_in_pad, p->C, 0))) break;
+    if ((st = alloc_packed(p, p->expand_flat, 1, p->k0_pad, p->C, 1))) break;
+    for (int i = 0; i < p->nb && !st; ++i) {
+      st = alloc_packed(p, p->conv[2 * i], p->taps[i + 1], p->C, p->C, 0);
+      if (!st) st = alloc_packed(p, p->conv[2 * i + 1], 1, p->C, p->C, 0);
+    }
+    if (st) break;
+    if ((st = alloc_packed(p, p->shrink, 1, p->C, p->c_out_pad, 0))) break;
+    // affine vectors: expand + 2*nb layers (C each) + shrink (c_out_pad)
+    float* aff = nullptr;
+    const size_t n_aff = (size_t)(2 * p->nb + 1) * 2 * p->C + 2 * p->c_out_pad;
+    if ((st = plan_alloc(p, reinterpret_cast<void**>(&aff), n_aff * sizeof(float)))) break;
+    p->expand_dil.scale = p->expand_flat.scale = aff;
+    p->expand_dil.shift = p->expand_flat.shift = aff + p->C;
+    for (int l = 0; l < 2 * p->nb; ++l) {
+      p->conv[l].scale = aff + (size_t)(l + 1) * 2 * p->C;
+      p->conv[l].shift = p->conv[l].scale + p->C;
+    }
+    p->shrink.scale = aff + (size_t)(2 * p->nb + 1) * 2 * p->C;
+    p->shrink.shift = p->shrink.scale + p->c_out_pad;
+  } while (0);
+  if (st) {
+    vp3d_plan_destroy(p);
+    return st;
+  }
+  *out_plan = p;
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void vp3d_plan_destroy(vp3d_plan* p) {
+  if (!p) return;
+  for (void* q : p->allocs) cudaFree(q);
+  if (p->d_x) cudaFree(p->d_x);
+  if (p->d_y) cudaFree(p->d_y);
+  if (p->d_ws) cudaFree(p->d_ws);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_receptive_field(const vp3d_plan* p) {
+  if (!p) return fail(VP3D_ERR_INVALID, "null plan");
+  int frames = 0;
+  for (int i = 0; i < p->cfg.num_widths; ++i) frames += p->pad[i];
+  return 1 + 2 * frames;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_total_causal_shift(const vp3d_plan* p) {
+  if (!p) return fail(VP3D_ERR_INVALID, "null plan");
+  const int* cs = p->cfg.variant == VP3D_VARIANT_STRIDED ? p->shift_str : p->shift_dil;
+  int frames = cs[0];
+  int next_dilation = p->cfg.filter_widths[0];
+  for (int i = 1; i < p->cfg.num_widths; ++i) {
+    frames += cs[i] * next_dilation;
+    next_dilation *= p->cfg.filter_widths[i];
+  }
+  return frames;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan* p, const vp3d_weights* w, int what, void* stream_) {
+  if (!p || !w) return fail(VP3D_ERR_INVALID, "set_weights: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int w0 = p->cfg.filter_widths[0];
+  if (what & VP3D_PACK_CONV) {
+    if (!w->expand_conv_weight || !w->shrink_weight)
+      return fail(VP3D_ERR_INVALID, "set_weights: missing conv weights");
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->C,
+                                     p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream));
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
+                                     p->c_in_raw, w0, p->C, p->k0_pad, 1, stream));
+    for (int i = 0; i < p->nb; ++i) {
+      if (!w->layers_conv_weight[2 * i] || !w->layers_conv_weight[2 * i + 1])
+        return fail(VP3D_ERR_INVALID, "set_weights: missing layers_conv.%d", 2 * i);
+      CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i], p->conv[2 * i].w, p->planes,
+                                       p->C, p->C, p->taps[i + 1], p->C, p->C, 0, stream));
+      CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i + 1], p->conv[2 * i + 1].w,
+                                       p->planes, p->C, p->C, 1, p->C, p->C, 0, stream));
+    }
+    CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw, p->C,
+                                     1, p->c_out_pad, p->C, 0, stream));
+    p->conv_packed = true;
+  }
+  if (what & VP3D_PACK_BN_EVAL) {
+    const float eps = 1e-5f;  // nn.BatchNorm1d default, model.py:32
+    for (int k = 0; k < 4; ++k)
+      if (!w->expand_bn[k]) return fail(VP3D_ERR_INVALID, "set_weights: missing expand_bn");
+    if (!w->shrink_bias) return fail(VP3D_ERR_INVALID, "set_weights: missing shrink.bias");
+    CUDA_TRY(launch_bn_fold(w->expand_bn[0], w->expand_bn[1], w->expand_bn[2], w->expand_bn[3], eps,
+                            p->expand_dil.scale, p->expand_dil.shift, p->C, p->C, stream));
+    for (int l = 0; l < 2 * p->nb; ++l) {
+      for (int k = 0; k < 4; ++k)
+        if (!w->layers_bn[l][k]) return fail(VP3D_ERR_INVALID, "set_weights: missing layers_bn.%d", l);
+      CUDA_TRY(launch_bn_fold(w->layers_bn[l][0], w->layers_bn[l][1], w->layers_bn[l][2],
+                              w->layers_bn[l][3], eps, p->conv[l].scale, p->conv[l].shift, p->C,
+                              p->C, stream));
+    }
+    CUDA_TRY(launch_bias_affine(w->shrink_bias, p->shrink.scale, p->shrink.shift, p->c_out_raw,
+                                p->c_out_pad, stream));
+    p->bn_packed = true;
+  }
+  return VP3D_OK;
+}
+
+// ------------------------------------------------------------------ eval schedules
+// The strided ("flat") schedule is used for TemporalModelOptimized1f and for TemporalModel in eval
+// mode when the input is exactly one receptive field long: with running statistics every output
+// frame depends only on its own dependency cone, whose rows are exactly the stride-w rows
+// Optimized1f computes (the reference states the weights are interchangeable, model.py:146-148).
+static bool use_strided(const vp3d_plan* p, int T) {
+  if (p->cfg.variant == VP3D_VARIANT_STRIDED) return true;
+  return !p->cfg.dense && T == vp3d_receptive_field(p);
+}
+
+// rows per sample after each stage: L[0] = rows out of expand, L[i] = rows out of block i
+static int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
+  const int* fw = p->cfg.filter_widths;
+  if (strided) {
+    L[0] = T / fw[0];  // Conv1d(stride=w, kernel=w): floor((T - w)/w) + 1
+    for (int i = 1; i <= p->nb; ++i) L[i] = L[i - 1] / fw[i];
+  } else {
+    L[0] = T - (fw[0] - 1);
+    for (int i = 1; i <= p->nb; ++i) L[i] = L[i - 1] - 2 * p->pad[i];
+  }
+  for (int i = 0; i <= p->nb; ++i)
+    if (L[i] < 1) return 0;
+  return L[p->nb];
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_output_frames(const vp3d_plan* p, int T) {
+  if (!p) return fail(VP3D_ERR_INVALID, "null plan");
+  int L[VP3D_MAX_WIDTHS];
+  return layer_rows(p, T, p->cfg.variant == VP3D_VARIANT_STRIDED, L);
+}
+
+struct WsLayout {
+  size_t a0 = 0, x0 = 0, x1 = 0, h = 0, total = 0;
+  size_t a0_plane = 0, x_plane = 0, h_plane = 0;  // elements per plane
+};
+
+static WsLayout ws_layout(const vp3d_plan* p, int N, int T, bool strided, const int* L) {
+  WsLayout w;
+  const size_t a0_rows = strided ? (size_t)N * L[0] : (size_t)N * T;
+  const size_t a0_ld = strided ? p->k0_pad : p->c_in_pad;
+  w.a0_plane = a0_rows * a0_ld;
+  w.x_plane = (size_t)N * L[0] * p->C;
+  w.h_plane = p->nb > 0 ? (size_t)N * L[1] * p->C : 0;
+  size_t off = 0;
+  w.a0 = off; off = align_up(off + w.a0_plane * p->planes * 2, 1024);
+  w.x0 = off; off = align_up(off + w.x_plane * p->planes * 2, 1024);
+  w.x1 = off; off = align_up(off + w.h_plane * p->planes * 2, 1024);  // block outputs are <= L[1] rows
+  w.h = off;  off = align_up(off + w.h_plane * p->planes * 2, 1024);
+  w.total = off + 1024;
+  return w;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t vp3d_workspace_bytes(const vp3d_plan* p, int N, int T) {
+  if (!p || N < 1) return 0;
+  int L[VP3D_MAX_WIDTHS];
+  const bool strided = use_strided(p, T);
+  if (!layer_rows(p, T, strided, L)) return 0;
+  return ws_layout(p, N, T, strided, L).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_plan* p, const float* x, float* y, int N, int T, void* ws,
+                                 size_t ws_bytes, void* stream_) {
+  if (!p || !x || !y) return fail(VP3D_ERR_INVALID, "forward_eval: null argument");
+  if (N < 1) return fail(VP3D_ERR_INVALID, "forward_eval: batch must be >= 1");
+  if (!p->conv_packed || !p->bn_packed)
+    return fail(VP3D_ERR_STATE, "forward_eval: vp3d_set_weights has not been called");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool strided = use_strided(p, T);
+  int L[VP3D_MAX_WIDTHS];
+  if (!layer_rows(p, T, strided, L))
+    return fail(VP3D_ERR_INVALID, "forward_eval: sequence of %d frames is shorter than the "
+                "receptive field (%d)", T, vp3d_receptive_field(p));
+  const WsLayout wl = ws_layout(p, N, T, strided, L);
+  if (!ws || ws_bytes < wl.total) return fail(VP3D_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+                                              ws_bytes, wl.total);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(base + wl.a0);
+  __nv_bfloat16* xb[2] = {reinterpret_cast<__nv_bfloat16*>(base + wl.x0),
+                          reinterpret_cast<__nv_bfloat16*>(base + wl.x1)};
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(base + wl.h);
+  const int* fw = p->cfg.filter_widths;
+  const int C = p->C;
+  int launches = 0;
+
+  vp3d_conv_desc d;
+  auto common = [&](vp3d_conv_desc& q) {
+    memset(&q, 0, sizeof(q));
+    q.a_planes = p->planes;
+    q.precision = p->cfg.precision;
+    q.out_planes = p->planes;
+    q.res_planes = p->planes;
+  };
+
+  // ---- input packing + expand conv (model.py:127 / :188)
+  if (strided) {
+    CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
+                               (long long)wl.a0_plane, stream));
+    ++launches;
+    common(d);
+    d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
+    d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
+    d.per_sample_tiles = 0; d.out_rows = N * L[0];
+  } else {
+    CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
+                               (long long)wl.a0_plane, stream));
+    ++launches;
+    common(d);
+    d.a = a0; d.samples = N; d.a_rows = T; d.a_ld = p->c_in_pad;
+    d.w = p->expand_dil.w; d.taps = fw[0]; d.k_per_tap = p->c_in_pad; d.n_pad = C;
+    d.per_sample_tiles = 1; d.tap_row_step = 1; d.out_rows = L[0];
+  }
+  d.scale = p->expand_dil.scale; d.shift = p->expand_dil.shift; d.relu = 1;
+  d.out = xb[0]; d.out_plane_stride = (long long)wl.x_plane; d.out_ld = C;
+  VP3D_TRY(run_conv(&d, stream));
+  ++launches;
+
+  // ---- residual blocks (model.py:129-135 / :190-194)
+  int cur = 0;
+  size_t cur_plane = wl.x_plane;
+  for (int i = 1; i <= p->nb; ++i) {
+    const PackedConv& c0 = p->conv[2 * (i - 1)];
+    const PackedConv& c1 = p->conv[2 * (i - 1) + 1];
+    const int Lin = L[i - 1], Lout = L[i];
+    const size_t h_plane = (size_t)N * Lout * C;
+    // first conv of the block: dilated / strided k-tap conv + BN + ReLU
+    common(d);
+    d.a = xb[cur];
+    d.w = c0.w; d.taps = c0.taps; d.k_per_tap = C; d.n_pad = C;
+    d.scale = c0.scale; d.shift = c0.shift; d.relu = 1;
+    d.out = hb; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
+    bool exact = false;
+    if (strided) {
+      exact = (Lin == fw[i] * Lout);
+      d.tap_col_step = C; d.tap_row_step = 0;
+      if (exact) {
+        d.samples = 1; d.a_rows = N * Lout; d.a_ld = fw[i] * C;
+        d.per_sample_tiles = 0; d.out_rows = N * Lout;
+      } else {
+        // trailing frames that do not fill a stride group are dropped (Conv1d floor semantics)
+        return fail(VP3D_ERR_UNSUPPORTED,
+                    "strided schedule needs layer lengths divisible by the filter width "
+                    "(block %d: %d frames, width %d)", i, Lin, fw[i]);
+      }
+    } else {
+      d.samples = N; d.a_rows = Lin; d.a_ld = C;
+      d.per_sample_tiles = 1; d.tap_row_step = p->dilation[i]; d.tap_col_step = 0;
+      d.out_rows = Lout;
+    }
+    // plane stride of A is implied by (samples, a_rows, a_ld) == cur_plane by construction
+    if ((size_t)d.samples * d.a_rows * d.a_ld != cur_plane)
+      return fail(VP3D_ERR_STATE, "internal: activation plane mismatch in block %d", i);
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+
+    // second conv: 1x1 + BN + ReLU + sliced residual
+    common(d);
+    d.a = hb; d.samples = 1; d.a_rows = N * Lout; d.a_ld = C;
+    d.w = c1.w; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
+    d.per_sample_tiles = 0; d.out_rows = N * Lout;
+    d.scale = c1.scale; d.shift = c1.shift; d.relu = 1;
+    d.res = xb[cur]; d.res_plane_stride = (long long)cur_plane; d.res_ld = C;
+    if (strided) {
+      d.res_rows_per_sample = 0; d.res_row_step = fw[i];
+      d.res_row_off = fw[i] / 2 + p->shift_str[i]; d.res_sample_div = 0;
+    } else {
+      d.res_rows_per_sample = Lin; d.res_row_step = 1;
+      d.res_row_off = p->pad[i] + p->shift_dil[i]; d.res_sample_div = Lout;
+    }
+    d.out = xb[cur ^ 1]; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+    cur ^= 1;
+    cur_plane = h_plane;
+  }
+
+  // ---- shrink (model.py:137 / :196) writing (N, T_out, J_out, 3) directly (fuses :74-75)
+  common(d);
+  d.a = xb[cur]; d.samples = 1; d.a_rows = N * L[p->nb]; d.a_ld = C;
+  d.w = p->shrink.w; d.taps = 1; d.k_per_tap = C; d.n_pad = p->c_out_pad;
+  d.per_sample_tiles = 0; d.out_rows = N * L[p->nb];
+  d.scale = p->shrink.scale; d.shift = p->shrink.shift; d.relu = 0;
+  d.out = nullptr; d.out_f32 = y; d.out_f32_ld = p->c_out_raw; d.n_valid = p->c_out_raw;
+  VP3D_TRY(run_conv(&d, stream));
+  ++launches;
+  p->last_launches = launches;
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host(vp3d_plan* p, const float* x_host, float* y_host, int N,
+                                      int T) {
+  if (!p || !x_host || !y_host) return fail(VP3D_ERR_INVALID, "forward_eval_host: null argument");
+  const int t_out = vp3d_output_frames(p, T);
+  if (t_out < 1 || N < 1) return fail(VP3D_ERR_INVALID, "forward_eval_host: bad shape");
+  if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  const size_t xb = (size_t)N * T * p->c_in_raw * sizeof(float);
+  const size_t yb = (size_t)N * t_out * p->c_out_raw * sizeof(float);
+  const size_t wb = vp3d_workspace_bytes(p, N, T);
+  if (xb > p->d_x_bytes) {
+    if (p->d_x) cudaFree(p->d_x);
+    p->d_x = nullptr; p->d_x_bytes = 0;
+    CUDA_TRY(cudaMalloc(&p->d_x, xb));
+    p->d_x_bytes = xb;
+  }
+  if (yb > p->d_y_bytes) {
+    if (p->d_y) cudaFree(p->d_y);
+    p->d_y = nullptr; p->d_y_bytes = 0;
+    CUDA_TRY(cudaMalloc(&p->d_y, yb));
+    p->d_y_bytes = yb;
+  }
+  if (wb > p->d_ws_bytes) {
+    if (p->d_ws) cudaFree(p->d_ws);
+    p->d_ws = nullptr; p->d_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&p->d_ws, wb));
+    p->d_ws_bytes = wb;
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->d_x, x_host, xb, cudaMemcpyHostToDevice, p->stream));
+  VP3D_TRY(vp3d_forward_eval(p, p->d_x, p->d_y, N, T, p->d_ws, p->d_ws_bytes, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(y_host, p->d_y, yb, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_last_launch_count(const vp3d_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" __attribute__((visibility("default"))) int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream) {
+  return run_conv(d, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,325 @@
+// tcgen05 implicit-GEMM kernel for the temporal convolutions.  See conv_gemm.cuh for the math.
+//
+// CTA = 256 threads, persistent over output tiles (128 rows x BLOCK_N channels):
+//   warp 0 lane 0 : TMA producer  (A tile 128x64 bf16 + W tile BLOCK_Nx64 bf16 per k-block)
+//   warp 1 lane 0 : tcgen05.mma issuer (4 x K=16 MMAs per k-block, accumulator in TMEM)
+//   warp 2        : TMEM allocator / deallocator
+//   warps 4..7    : epilogue (tcgen05.ld -> BN affine / ReLU / residual / stats -> global)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace vp3d {
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+  static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
+};
+
+__device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
+                                            int& sample, int& row0) {
+  n_blk = tile % p.n_tiles;
+  int m_blk = tile / p.n_tiles;
+  if (p.dilated) {
+    sample = m_blk / p.tiles_per_sample;
+    row0 = (m_blk - sample * p.tiles_per_sample) * kBlockM;
+  } else {
+    sample = 0;
+    row0 = m_blk * kBlockM;
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_w, const ConvGemmArgs p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + kStages * Cfg::kABytes;
+  const uint32_t bar_base = base + kStages * Cfg::kStageBytes;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + kStages * 8;
+  const uint32_t tfull_bar = bar_base + 2 * kStages * 8;
+  const uint32_t tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = p.dilated ? p.samples * p.tiles_per_sample : p.tiles_per_sample;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int k_iters = p.pairs * p.taps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s * 8, 1);
+      mbar_init(empty_bar + s * 8, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s * 8, 1);
+      mbar_init(tempty_bar + s * 8, 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_blk, sample, row0;
+        tile_coords(p, tile, n_blk, sample, row0);
+        for (int pair = 0; pair < p.pairs; ++pair) {
+          const int a_plane = (pair == 1) ? 1 : 0;
+          const int w_plane = (pair == 2) ? 1 : 0;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int a_row = row0 + tap * p.tap_row_step;
+            const int a_col0 = tap * p.tap_col_step;
+            const int w_row = (w_plane * p.taps + tap) * p.n_pad + n_blk * BLOCK_N;
+            for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+              mbar_wait(empty_bar + stage * 8, phase ^ 1);
+              mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
+              tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
+                          a_col0 + kb * kBlockK, a_row, sample, a_plane);
+              tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
+                          kb * kBlockK, w_row);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar + stage * 8, phase);
+          tc_fence_after();
+          const uint64_t desc_a = make_smem_desc_k_sw128(smem_a + stage * Cfg::kABytes);
+          const uint64_t desc_b = make_smem_desc_k_sw128(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+            umma_bf16_ss(d_tmem, desc_a + 2 * k, desc_b + 2 * k, idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage * 8);  // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + acc * 8);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int r_in_tile = ew * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    const bool do_relu = p.flags & kEpiRelu;
+    const bool do_res = p.flags & kEpiResidual;
+    const bool do_stats = p.flags & kEpiStats;
+    const bool do_f32 = p.flags & kEpiOutF32;
+    const bool do_affine = p.flags & kEpiAffine;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_blk, sample, row0;
+      tile_coords(p, tile, n_blk, sample, row0);
+      const int t = row0 + r_in_tile;
+      const bool valid = t < p.out_rows;
+      const long long out_row = (long long)sample * p.out_rows + t;
+      long long res_row;
+      if (!p.dilated && p.res_sample_div > 0) {
+        const int rs = t / p.res_sample_div;
+        const int rt = t - rs * p.res_sample_div;
+        res_row = (long long)rs * p.res_rows_per_sample + (long long)rt * p.res_row_step +
+                  p.res_row_off;
+      } else {
+        res_row = (long long)sample * p.res_rows_per_sample + (long long)t * p.res_row_step +
+                  p.res_row_off;
+      }
+
+      mbar_wait(tfull_bar + acc * 8, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(t_addr + chunk * 32, raw);
+        tmem_ld_wait();
+        const int c0 = n_blk * BLOCK_N + chunk * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+
+        if (do_affine) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+            v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
+            v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+            v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+            v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+          }
+        }
+        if (do_relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (do_res && valid) {
+          const __nv_bfloat16* rp = p.res + res_row * p.res_ld + c0;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            if (pl < p.res_planes) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(r4 + q);
+                v[q * 8 + 0] += bf16_lo_to_f(u.x);
+                v[q * 8 + 1] += bf16_hi_to_f(u.x);
+                v[q * 8 + 2] += bf16_lo_to_f(u.y);
+                v[q * 8 + 3] += bf16_hi_to_f(u.y);
+                v[q * 8 + 4] += bf16_lo_to_f(u.z);
+                v[q * 8 + 5] += bf16_hi_to_f(u.z);
+                v[q * 8 + 6] += bf16_lo_to_f(u.w);
+                v[q * 8 + 7] += bf16_hi_to_f(u.w);
+              }
+            }
+          }
+        }
+        if (do_f32) {
+          if (valid) {
+            float* op = p.out_f32 + out_row * p.out_f32_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.n_valid) op[j] = v[j];
+          }
+        } else if (valid) {
+          __nv_bfloat16* op = p.out + out_row * p.out_ld + c0;
+          uint32_t hi[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o4[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (p.out_planes == 2) {
+            uint32_t lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float r0 = v[2 * j] - bf16_lo_to_f(hi[j]);
+              const float r1 = v[2 * j + 1] - bf16_hi_to_f(hi[j]);
+              lo[j] = pack_bf16x2(r0, r1);
+            }
+            uint4* l4 = reinterpret_cast<uint4*>(op + p.out_plane_stride);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              l4[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        }
+        if (do_stats) {
+          // Per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce,
+          // 31 shuffles per statistic; afterwards lane j owns channel c0 + j.
+          float s[32], q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = valid ? v[j] : 0.0f;
+            s[j] = x;
+            q[j] = x * x;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = lane & off;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = upper ? s[i] : s[i + off];
+              const float keep_s = upper ? s[i + off] : s[i];
+              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              const float send_q = upper ? q[i] : q[i + off];
+              const float keep_q = upper ? q[i + off] : q[i];
+              q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          atomicAdd(p.stats + c0 + lane, s[0]);
+          atomicAdd(p.stats + p.n_pad + c0 + lane, q[0]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + acc * 8);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
+                               const ConvGemmArgs& args, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
+  const int total = m_tiles * args.n_tiles;
+  if (total <= 0) return cudaSuccess;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
+                             const ConvGemmArgs& args, int block_n, int num_sms,
+                             cudaStream_t stream) {
+  switch (block_n) {
+    case 256: return launch_impl<256>(tmap_a, tmap_w, args, num_sms, stream);
+    case 128: return launch_impl<128>(tmap_a, tmap_w, args, num_sms, stream);
+    case 64: return launch_impl<64>(tmap_a, tmap_w, args, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vp3d

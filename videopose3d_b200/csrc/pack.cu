@@ -1,0 +1,131 @@
+#include "pack.cuh"
+
+#include <stdint.h>
+
+namespace vp3d {
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// One thread per (row, 8-column group): 16-byte stores, coalesced along the row.
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                  int planes, int N, int T, int c_raw, int rows, int group,
+                                  int frame_step, int k_pad, long long plane_stride) {
+  const int groups_per_row = k_pad >> 3;
+  const long long total = (long long)N * rows * groups_per_row;
+  const int k_valid = group * c_raw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups_per_row);
+    const long long row = i / groups_per_row;
+    const int r = (int)(row % rows);
+    const int n = (int)(row / rows);
+    const float* src = x + ((long long)n * T + (long long)r * frame_step) * c_raw;
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      const float v = (k < k_valid) ? __ldg(src + k) : 0.0f;
+      split_bf16(v, hi[j], lo[j]);
+    }
+    __nv_bfloat16* dst = out + row * k_pad + g * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
+                              int c_raw, int rows, int group, int frame_step, int k_pad,
+                              long long plane_stride, cudaStream_t stream) {
+  const long long total = (long long)N * rows * (k_pad >> 3);
+  if (total <= 0) return cudaSuccess;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_input_kernel<<<(int)blocks, threads, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
+                                                         frame_step, k_pad, plane_stride);
+  return cudaGetLastError();
+}
+
+// One thread per output element pair is plenty: weights are repacked once per optimizer step at most.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                        int planes, int c_out, int c_in, int taps, int n_pad,
+                                        int k_pad, int merge_taps) {
+  const int taps_out = merge_taps ? 1 : taps;
+  const long long plane_elems = (long long)taps_out * n_pad * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane_elems;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % k_pad);
+    const int co = (int)((i / k_pad) % n_pad);
+    const int tp = (int)(i / ((long long)k_pad * n_pad));
+    float v = 0.0f;
+    if (co < c_out) {
+      if (merge_taps) {
+        if (k < taps * c_in) {
+          const int tap = k / c_in, ci = k - tap * c_in;
+          v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
+        }
+      } else if (k < c_in) {
+        v = __ldg(w + ((long long)co * c_in + k) * taps + tp);
+      }
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    out[i] = hi;
+    if (planes == 2) out[plane_elems + i] = lo;
+  }
+}
+
+cudaError_t launch_pack_conv_weight(const float* w, __nv_bfloat16* out, int planes, int c_out,
+                                    int c_in, int taps, int n_pad, int k_pad, int merge_taps,
+                                    cudaStream_t stream) {
+  const long long total = (long long)(merge_taps ? 1 : taps) * n_pad * k_pad;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_conv_weight_kernel<<<(int)blocks, threads, 0, stream>>>(w, out, planes, c_out, c_in, taps,
+                                                               n_pad, k_pad, merge_taps);
+  return cudaGetLastError();
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, float* __restrict__ scale, float* __restrict__ shift,
+                               int c, int c_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_pad) return;
+  float s = 0.0f, b = 0.0f;
+  if (i < c) {
+    s = gamma[i] / sqrtf(var[i] + eps);
+    b = beta[i] - mean[i] * s;
+  }
+  scale[i] = s;
+  shift[i] = b;
+}
+
+cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* mean,
+                           const float* var, float eps, float* scale, float* shift, int c,
+                           int c_pad, cudaStream_t stream) {
+  bn_fold_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift,
+                                                          c, c_pad);
+  return cudaGetLastError();
+}
+
+__global__ void bias_affine_kernel(const float* __restrict__ bias, float* __restrict__ scale,
+                                   float* __restrict__ shift, int c, int c_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_pad) return;
+  scale[i] = (i < c) ? 1.0f : 0.0f;
+  shift[i] = (i < c) ? bias[i] : 0.0f;
+}
+
+cudaError_t launch_bias_affine(const float* bias, float* scale, float* shift, int c, int c_pad,
+                               cudaStream_t stream) {
+  bias_affine_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(bias, scale, shift, c, c_pad);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d
