@@ -117,6 +117,13 @@ int vp3d_forward_eval_host(vp3d_plan* plan, const float* x_host, float* y_host, 
 /* Number of kernels the last forward on this plan launched (for bench.py's gpu_launches). */
 int vp3d_last_launch_count(const vp3d_plan* plan);
 
+/* Measurement hook (bench.py roofline): bracket launch number `launch_index` (0-based position in
+ * the forward's launch sequence, -1 = off) of every following forward with CUDA events recorded on
+ * the forward's own stream.  vp3d_profile_read synchronises those events, returns the summed
+ * duration in milliseconds and the number of bracketed launches, and resets the accumulator. */
+int vp3d_profile_launch(vp3d_plan* plan, int launch_index);
+int vp3d_profile_read(vp3d_plan* plan, float* total_ms, int* count);
+
 /* ---- operator-level entry (used by the parity tests; the model-level calls are built on it) ----
  * One temporal convolution on channel-last bf16 activations with the fused epilogue.
  * Replaces nn.Conv1d (+ BatchNorm1d eval affine + ReLU + residual slice-add), model.py:127, 134-135. */

@@ -1,0 +1,109 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vp3d_b200.h declares; the Python
+module mirrors the reference's nn.Module contract (constructor, attributes, state_dict layout) and
+refuses to compute without CUDA (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+import videopose3d_b200 as vp
+from videopose3d_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "vp3d_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vp3d_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_capi.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    lib = _capi.load()
+    declared = _declared_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.vp3d_version() == 100
+    assert sorted(_capi.SIGNATURES) == declared
+
+
+def test_struct_sizes_match_header_layout():
+    # vp3d_config: 4 ints + int[8] + 5 ints
+    assert _capi.ctypes.sizeof(_capi.Config) == 4 * (4 + 8 + 5)
+    # vp3d_weights: 1 + 4 + 14 + 14*4 + 2 pointers
+    assert _capi.ctypes.sizeof(_capi.Weights) == 8 * (1 + 4 + 14 + 56 + 2)
+
+
+def test_plan_create_reports_errors_without_gpu():
+    lib = _capi.load()
+    cfg = _capi.Config()
+    cfg.num_joints_in, cfg.in_features, cfg.num_joints_out = 17, 2, 17
+    cfg.num_widths = 2
+    cfg.filter_widths[0], cfg.filter_widths[1] = 3, 4
+    cfg.channels = 1024
+    h = _capi.ctypes.c_void_p()
+    st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
+    assert st == -1 and b"odd filter widths" in lib.vp3d_last_error()
+    cfg.filter_widths[1] = 3
+    cfg.channels = 100
+    st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
+    assert st == -2 and b"multiple of 64" in lib.vp3d_last_error()
+    if not torch.cuda.is_available():
+        cfg.channels = 128
+        st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
+        assert st == -3  # VP3D_ERR_CUDA: reported, not a crash and not a CPU fallback
+
+
+@pytest.mark.parametrize("cls,kw", [
+    (vp.TemporalModel, dict(filter_widths=[3, 3, 3], causal=False)),
+    (vp.TemporalModel, dict(filter_widths=[3, 5, 3], causal=True, channels=128)),
+    (vp.TemporalModel, dict(filter_widths=[3, 3], dense=True, channels=64)),
+    (vp.TemporalModelOptimized1f, dict(filter_widths=[3, 3, 3, 3, 3], causal=False)),
+    (vp.TemporalModelOptimized1f, dict(filter_widths=[3, 3, 3], causal=True, channels=256)),
+])
+def test_module_contract(cls, kw):
+    """Key set / order / shapes of the state_dict and the derived attributes."""
+    from oracle import temporal_model_oracle as orc
+    m = cls(17, 2, 17, **kw)
+    C = kw.get("channels", 1024)
+    fw = kw["filter_widths"]
+    nb = len(fw) - 1
+    strided = cls is vp.TemporalModelOptimized1f
+    a = orc.arch(fw, causal=kw.get("causal", False), dense=kw.get("dense", False), strided=strided)
+    keys = list(m.state_dict().keys())
+    bn = lambda p: [f"{p}.weight", f"{p}.bias", f"{p}.running_mean", f"{p}.running_var",
+                    f"{p}.num_batches_tracked"]
+    expect = bn("expand_bn") + ["shrink.weight", "shrink.bias", "expand_conv.weight"] + \
+        [f"layers_conv.{i}.weight" for i in range(2 * nb)] + \
+        sum((bn(f"layers_bn.{i}") for i in range(2 * nb)), [])
+    assert keys == expect
+    sd = m.state_dict()
+    assert tuple(sd["expand_conv.weight"].shape) == (C, 34, fw[0])
+    assert tuple(sd["shrink.weight"].shape) == (51, C, 1) and tuple(sd["shrink.bias"].shape) == (51,)
+    for i in range(nb):
+        assert tuple(sd[f"layers_conv.{2 * i}.weight"].shape) == (C, C, a["taps"][i + 1])
+        assert tuple(sd[f"layers_conv.{2 * i + 1}.weight"].shape) == (C, C, 1)
+    assert sd["expand_bn.num_batches_tracked"].dtype == torch.int64
+    assert m.pad == a["pad"] and m.causal_shift == a["shift"]
+    assert m.receptive_field() == a["receptive_field"]
+    assert isinstance(m.drop, torch.nn.Dropout) and isinstance(m.relu, torch.nn.ReLU)
+    m.set_bn_momentum(0.03)
+    assert m.expand_bn.momentum == 0.03 and all(b.momentum == 0.03 for b in m.layers_bn)
+    # the oracle's seeded parameters load into the module (same layout as the reference's)
+    m.load_state_dict(orc.make_state_dict(17, 2, 17, fw, C, dense=kw.get("dense", False)))
+
+
+def test_no_cpu_fallback():
+    m = vp.TemporalModel(17, 2, 17, [3, 3, 3], channels=64).eval()
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 27, 17, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 27, 17, 2))
+    with pytest.raises(AssertionError, match="odd filter widths"):
+        vp.TemporalModelOptimized1f(17, 2, 17, [3, 2])

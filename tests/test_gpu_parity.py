@@ -46,16 +46,41 @@ def test_golden_eval_fp32_faithful(cuda_device, name):
 
 @pytest.mark.parametrize("name", EVAL_CASES)
 def test_golden_eval_bf16(cuda_device, name):
+    """bf16 fast mode against the reference goldens: bounded relative error (bf16 operands through
+    2B+2 layers) and mpjpe(new, ref) below 1% of the output scale.  The 0.1 mm MPJPE-shift gate
+    needs thousands of joints to be a statistic rather than noise: see test_bf16_mpjpe_gate."""
     meta, sd, x, y_ref, _ = load_golden(name)
     m = _build(meta, sd, cuda_device, "bf16")
     with torch.no_grad():
         y = m(x.to(cuda_device)).cpu()
     assert _rel(y.numpy(), y_ref) <= 3e-2
-    g = torch.Generator().manual_seed(5)
     ref = torch.from_numpy(y_ref)
+    scale = float(torch.norm(ref, dim=-1).mean())
+    assert float(orc.mpjpe(y, ref)) <= 1e-2 * scale
+
+
+def test_bf16_mpjpe_gate(cuda_device):
+    """G2 at BASELINE configs[1] size (N = 1024 windows -> 17408 joints): MPJPE of the bf16 path
+    against synthetic targets y = ref + N(0, 30 mm) differs from the reference's MPJPE by <= 0.1 mm
+    (outputs read as metres).  `ref` here is the fp32-faithful CUDA path, itself pinned to the
+    reference goldens at <= 1e-3 by test_golden_eval_fp32_faithful."""
+    meta, sd, x8, y_ref, _ = load_golden("cfg2_tm_33333_c1024")
+    x = orc.make_input(1024, 243, seed=78)
+    x[:8] = x8
+    xg = x.to(cuda_device)
+    m = _build(meta, sd, cuda_device, "bf16x3")
+    with torch.no_grad():
+        ref = m(xg).cpu()
+        y = m.set_precision("bf16")(xg).cpu()
+    assert _rel(ref[:8].numpy(), y_ref) <= 1e-3
+    g = torch.Generator().manual_seed(5)
     target = ref + torch.randn(ref.shape, generator=g) * 0.03
-    d_mm = abs(float(orc.mpjpe(y, target)) - float(orc.mpjpe(ref, target))) * 1000
-    assert d_mm <= 0.1, f"MPJPE shift {d_mm:.4f} mm"
+    target[:, :, 0] = ref[:, :, 0]
+    e_new, e_ref = float(orc.mpjpe(y, target)) * 1000, float(orc.mpjpe(ref, target)) * 1000
+    direct = float(orc.mpjpe(y, ref)) * 1000
+    print(f"MPJPE(ref,y)={e_ref:.3f} mm  MPJPE(bf16,y)={e_new:.3f} mm  mpjpe(bf16,ref)={direct:.3f} mm "
+          f"output scale {float(torch.norm(ref, dim=-1).mean()):.3f}")
+    assert abs(e_new - e_ref) <= 0.1
 
 
 def test_output_is_fresh_writable_tensor(cuda_device):

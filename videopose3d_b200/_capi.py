@@ -106,6 +106,9 @@ SIGNATURES = {
     "vp3d_forward_eval_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int, ctypes.c_int]),
     "vp3d_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "vp3d_profile_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "vp3d_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
+                                         ctypes.POINTER(ctypes.c_int)]),
     "vp3d_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
 }
 

@@ -217,6 +217,10 @@ struct vp3d_plan {
   size_t d_x_bytes = 0, d_y_bytes = 0, d_ws_bytes = 0;
   cudaStream_t stream = nullptr;
   int last_launches = 0;
+  // measurement hook: event pairs around one chosen launch of each forward
+  int prof_launch = -1;
+  std::vector<cudaEvent_t> prof_events;  // start/stop pairs
+  size_t prof_used = 0;                  // events consumed since the last read
 };
 
 static int plan_alloc(vp3d_plan* p, void** out, size_t bytes) {
@@ -326,6 +330,7 @@ extern "C" __attribute__((visibility("default"))) void vp3d_plan_destroy(vp3d_pl
   if (p->d_y) cudaFree(p->d_y);
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->stream) cudaStreamDestroy(p->stream);
+  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   delete p;
 }
 
@@ -475,6 +480,26 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   const int* fw = p->cfg.filter_widths;
   const int C = p->C;
   int launches = 0;
+  // measurement hook: record an event pair around launch number p->prof_launch
+  auto prof_event = [&](bool begin) -> int {
+    if (p->prof_launch < 0 || launches != p->prof_launch) return VP3D_OK;
+    const size_t idx = p->prof_used + (begin ? 0 : 1);
+    while (p->prof_events.size() <= idx) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      p->prof_events.push_back(e);
+    }
+    CUDA_TRY(cudaEventRecord(p->prof_events[idx], stream));
+    if (!begin) p->prof_used += 2;
+    return VP3D_OK;
+  };
+#define VP3D_LAUNCH(call)          \
+  do {                             \
+    VP3D_TRY(prof_event(true));    \
+    call;                          \
+    VP3D_TRY(prof_event(false));   \
+    ++launches;                    \
+  } while (0)
 
   vp3d_conv_desc d;
   auto common = [&](vp3d_conv_desc& q) {
@@ -487,17 +512,15 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
 
   // ---- input packing + expand conv (model.py:127 / :188)
   if (strided) {
-    CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
-                               (long long)wl.a0_plane, stream));
-    ++launches;
+    VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
+                               (long long)wl.a0_plane, stream)));
     common(d);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
     d.per_sample_tiles = 0; d.out_rows = N * L[0];
   } else {
-    CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
-                               (long long)wl.a0_plane, stream));
-    ++launches;
+    VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
+                               (long long)wl.a0_plane, stream)));
     common(d);
     d.a = a0; d.samples = N; d.a_rows = T; d.a_ld = p->c_in_pad;
     d.w = p->expand_dil.w; d.taps = fw[0]; d.k_per_tap = p->c_in_pad; d.n_pad = C;
@@ -505,8 +528,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   }
   d.scale = p->expand_dil.scale; d.shift = p->expand_dil.shift; d.relu = 1;
   d.out = xb[0]; d.out_plane_stride = (long long)wl.x_plane; d.out_ld = C;
-  VP3D_TRY(run_conv(&d, stream));
-  ++launches;
+  VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
 
   // ---- residual blocks (model.py:129-135 / :190-194)
   int cur = 0;
@@ -543,8 +565,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     // plane stride of A is implied by (samples, a_rows, a_ld) == cur_plane by construction
     if ((size_t)d.samples * d.a_rows * d.a_ld != cur_plane)
       return fail(VP3D_ERR_STATE, "internal: activation plane mismatch in block %d", i);
-    VP3D_TRY(run_conv(&d, stream));
-    ++launches;
+    VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
 
     // second conv: 1x1 + BN + ReLU + sliced residual
     common(d);
@@ -561,8 +582,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       d.res_row_off = p->pad[i] + p->shift_dil[i]; d.res_sample_div = Lout;
     }
     d.out = xb[cur ^ 1]; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
-    VP3D_TRY(run_conv(&d, stream));
-    ++launches;
+    VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
     cur ^= 1;
     cur_plane = h_plane;
   }
@@ -574,8 +594,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   d.per_sample_tiles = 0; d.out_rows = N * L[p->nb];
   d.scale = p->shrink.scale; d.shift = p->shrink.shift; d.relu = 0;
   d.out = nullptr; d.out_f32 = y; d.out_f32_ld = p->c_out_raw; d.n_valid = p->c_out_raw;
-  VP3D_TRY(run_conv(&d, stream));
-  ++launches;
+  VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
   p->last_launches = launches;
   return VP3D_OK;
 }
@@ -615,6 +634,29 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host(vp3
 }
 
 extern "C" __attribute__((visibility("default"))) int vp3d_last_launch_count(const vp3d_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" __attribute__((visibility("default"))) int vp3d_profile_launch(vp3d_plan* p, int launch_index) {
+  if (!p) return fail(VP3D_ERR_INVALID, "null plan");
+  p->prof_launch = launch_index;
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_profile_read(vp3d_plan* p, float* total_ms, int* count) {
+  if (!p || !total_ms || !count) return fail(VP3D_ERR_INVALID, "profile_read: null argument");
+  float sum = 0.0f;
+  int n = 0;
+  for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+    CUDA_TRY(cudaEventSynchronize(p->prof_events[i + 1]));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->prof_events[i], p->prof_events[i + 1]));
+    sum += ms;
+    ++n;
+  }
+  p->prof_used = 0;
+  *total_ms = sum;
+  *count = n;
+  return VP3D_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream) {
   return run_conv(d, static_cast<cudaStream_t>(stream));
