@@ -262,7 +262,9 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32-faithful)",
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)",
+                      "mixed": "bf16 (FLOP-dominant blocks plain bf16; expand/shrink/tail blocks "
+                               "split-bf16; fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {
                 "workload": "TemporalModel arc=3,3,3,3,3 T=243 C=1024 J=17 eval forward, N=1024 "
@@ -313,7 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

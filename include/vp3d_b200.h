@@ -42,7 +42,10 @@ typedef enum {
 
 typedef enum {
   VP3D_PRECISION_BF16 = 0,   /* bf16 operands, fp32 accumulate (fast path; BASELINE cfg 2) */
-  VP3D_PRECISION_BF16X3 = 1  /* split-bf16 (hi+lo) operands, 3 MMAs per product: fp32-faithful */
+  VP3D_PRECISION_BF16X3 = 1, /* split-bf16 (hi+lo) operands, 3 MMAs per product: fp32-faithful */
+  VP3D_PRECISION_MIXED = 2   /* eval default: bf16 on the FLOP-dominant blocks, split-bf16 on the
+                                cheap layers (expand, shrink, narrow tail blocks), residual stream
+                                kept in hi+lo planes; <= 1e-3 of fp32 at ~bf16 cost */
 } vp3d_precision;
 
 /* Constructor arguments of TemporalModel / TemporalModelOptimized1f (model.py:85-86, :151-152). */
@@ -92,6 +95,7 @@ int vp3d_total_causal_shift(const vp3d_plan* plan);
  * (scale = w / sqrt(running_var + 1e-5), shift = b - running_mean * scale) and shrink bias. */
 #define VP3D_PACK_CONV 1
 #define VP3D_PACK_BN_EVAL 2
+#define VP3D_PACK_CONV_T 4 /* transposed conv weights for the data-gradient GEMMs (training only) */
 int vp3d_set_weights(vp3d_plan* plan, const vp3d_weights* w, int what, void* stream);
 
 /* Output frames for an input of T frames: T - receptive_field + 1 for the dilated variant
@@ -113,6 +117,37 @@ int vp3d_forward_eval(vp3d_plan* plan, const float* x, float* y, int N, int T, v
  * synchronises.  Device staging buffers are owned by the plan.  x_host / y_host should be pinned
  * for full PCIe bandwidth but pageable memory is accepted. */
 int vp3d_forward_eval_host(vp3d_plan* plan, const float* x_host, float* y_host, int N, int T);
+
+/* ---- training (TemporalModelOptimized1f; run.py:318-420) ------------------------------------
+ * Gradient buffers, one per learnable tensor of the state_dict (same shapes, fp32, device).  They
+ * are OVERWRITTEN by vp3d_backward (autograd accumulates them into .grad on the Python side). */
+typedef struct {
+  float* expand_conv_weight;
+  float* expand_bn[2]; /* weight, bias */
+  float* layers_conv_weight[VP3D_MAX_LAYERS];
+  float* layers_bn[VP3D_MAX_LAYERS][2];
+  float* shrink_weight;
+  float* shrink_bias;
+} vp3d_grads;
+
+/* Device scratch for one training step: saved activations for backward + gradient scratch. */
+size_t vp3d_train_workspace_bytes(const vp3d_plan* plan, int N, int T);
+
+/* Replaces TemporalModelOptimized1f.forward in train() mode (model.py:187-197 with BatchNorm batch
+ * statistics and Dropout active).  w: gamma / beta are read, running_mean / running_var are UPDATED
+ * in place with bn_momentum[l] (l = 0 expand_bn, 1.. = layers_bn[l-1]; host array of 1 + 2B floats,
+ * read at call time, model.py:36-39).  Conv weights must have been packed with
+ * VP3D_PACK_CONV | VP3D_PACK_CONV_T since their last update.  Dropout masks come from a counter-based
+ * generator keyed by `seed` (statistically, not bitwise, equal to torch's).  `workspace` must stay
+ * untouched until the matching vp3d_backward. */
+int vp3d_forward_train(vp3d_plan* plan, const float* x, float* y, int N, int T, const vp3d_weights* w,
+                       const float* bn_momentum, float dropout_p, unsigned long long seed,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces autograd's backward through the model (run.py:394, 418): dy is (N, T_out, J_out, 3) fp32;
+ * writes every parameter gradient.  Uses the activations saved by the last vp3d_forward_train. */
+int vp3d_backward(vp3d_plan* plan, const float* dy, const vp3d_grads* grads, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* Number of kernels the last forward on this plan launched (for bench.py's gpu_launches). */
 int vp3d_last_launch_count(const vp3d_plan* plan);
@@ -157,6 +192,9 @@ typedef struct {
   int res_row_step;
   int res_row_off;
   int res_sample_div;   /* flat tiling only: rows per sample used to split row -> (sample, t); 0 = none */
+  int res_col_begin;    /* residual only for output columns [res_col_begin, res_col_begin + res_cols) */
+  int res_cols;         /*   (0 = all columns); used by the dgrad skip-connection path */
+  int res_check_rows;   /* 1: ignore residual rows mapping outside [0, res_rows_per_sample) */
   void* out;            /* bf16 [out_planes][rows][out_ld] or NULL */
   int out_planes;
   long long out_plane_stride; /* elements */

@@ -35,6 +35,9 @@ def load_golden(name):
                                  dense=meta["dense"], seed=meta["seed"])
         x = orc.make_input(meta["N"], meta["T"], meta["J"], meta["F"], seed=meta["seed"] + 1)
     new = {k[4:]: z[k] for k in z.files if k.startswith("new/")}
+    if "gy" in z.files:
+        new["gy"] = z["gy"]
+        new.update({k: z[k] for k in z.files if k.startswith("grad/")})
     return meta, sd, x, z["y"], new
 
 

@@ -48,6 +48,10 @@ CASES = {
                              train=True, momentum=0.07),
     "opt_333_c64_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64,
                               N=6, T=27, train=True, momentum=0.1),
+    "opt_333_c128_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=128,
+                               N=40, T=27, train=True, momentum=0.05),
+    "opt_35_c128_train_causal": dict(cls="TemporalModelOptimized1f", J=16, F=2, Jout=16, fw=[3, 5],
+                                     C=128, N=70, T=15, train=True, momentum=0.1, causal=True),
     # BASELINE configs[0]: arc 3,3,3, 17 joints, N=64, CPU fp32 forward (C = 1024)
     "cfg1_tm_333_c1024": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=1024, N=64,
                               T=27, store_sd=False),
@@ -80,7 +84,14 @@ def build_case(name, cfg):
     if cfg.get("train"):
         model.train()
         model.set_bn_momentum(cfg["momentum"])
-        y = model(x).detach()
+        y_t = model(x)
+        # upstream gradient for the backward goldens: loss = sum(y * gy)
+        gy = torch.randn(y_t.shape, generator=torch.Generator().manual_seed(seed + 2))
+        (y_t * gy).sum().backward()
+        out["gy"] = gy.numpy()
+        for k, prm in model.named_parameters():
+            out["grad/" + k] = prm.grad.numpy()
+        y = y_t.detach()
         new_sd = model.state_dict()
         for k, v in new_sd.items():
             if "running" in k or "num_batches" in k:

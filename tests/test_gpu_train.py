@@ -1,0 +1,158 @@
+"""GPU: training-mode parity of TemporalModelOptimized1f (forward with BatchNorm batch statistics,
+running-stat update, backward for every parameter) against goldens produced by the real reference
+(forward output, updated running stats, autograd gradients; dropout = 0).
+
+Gates: bf16x3 (fp32-faithful) mode: max|new - ref| / max|ref| <= 1e-3 on the
+output, every parameter gradient and the post-step running statistics.  bf16 mode: <= 5e-2.
+Dropout (p > 0) is statistically equal to torch's, not bitwise: checked through keep-rate /
+determinism properties and a directional finite-difference check of the gradients."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+import videopose3d_b200 as vp
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_CASES = [n for n in golden_names() if n.startswith("opt") and "train" in n]
+
+
+def _build(meta, sd, dev, precision, dropout=0.0):
+    m = vp.TemporalModelOptimized1f(meta["J"], meta["F"], meta["Jout"], filter_widths=meta["fw"],
+                                    causal=meta["causal"], dropout=dropout, channels=meta["C"])
+    m.load_state_dict(sd)
+    m = m.to(dev).train().set_train_precision(precision)
+    m.set_bn_momentum(meta.get("momentum", 0.1))
+    return m
+
+
+def _rel(a, b):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else a
+    return float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_step_matches_reference(cuda_device, name, precision, tol):
+    meta, sd, x, y_ref, new = load_golden(name)
+    m = _build(meta, sd, cuda_device, precision)
+    y = m(x.to(cuda_device))
+    assert y.requires_grad and tuple(y.shape) == y_ref.shape
+    assert _rel(y, y_ref) <= tol
+    (y * torch.from_numpy(new["gy"]).to(cuda_device)).sum().backward()
+    worst = {}
+    for k, prm in m.named_parameters():
+        assert prm.grad is not None, k
+        worst[k] = _rel(prm.grad, new["grad/" + k])
+    bad = {k: v for k, v in worst.items() if not v <= tol}
+    assert not bad, f"gradient mismatch: {bad}"
+    sd_new = m.state_dict()
+    for k, v in new.items():
+        if k == "gy" or k.startswith("grad/"):
+            continue
+        if k.endswith("num_batches_tracked"):
+            assert int(sd_new[k]) == int(v)
+        else:
+            assert _rel(sd_new[k], v) <= tol, k
+
+
+def test_gradients_accumulate_and_eval_sees_new_stats(cuda_device):
+    meta, sd, x, y_ref, new = load_golden("opt_333_c128_train")
+    m = _build(meta, sd, cuda_device, "bf16x3")
+    xg = x.to(cuda_device)
+    gy = torch.from_numpy(new["gy"]).to(cuda_device)
+    (m(xg) * gy).sum().backward()
+    g1 = m.shrink.weight.grad.clone()
+    m.load_state_dict(sd)                       # restore running stats, keep .grad
+    (m(xg) * gy).sum().backward()               # autograd accumulates into .grad
+    assert _rel(m.shrink.weight.grad, (2 * g1).cpu().numpy()) <= 1e-5
+    # eval after training must use the updated running statistics
+    from oracle import temporal_model_oracle as orc
+    m.eval().set_precision("bf16x3")
+    with torch.no_grad():
+        y_eval = m(xg)
+    sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    y_o = orc.forward_numpy(sd_now, x.numpy(), meta["fw"], causal=meta["causal"], strided=True)
+    assert _rel(y_eval, y_o) <= 1e-3
+
+
+def test_dropout_statistics_and_determinism(cuda_device):
+    meta, sd, x, _, _ = load_golden("opt_333_c128_train")
+    xg = x.to(cuda_device)
+    m = _build(meta, sd, cuda_device, "bf16x3", dropout=0.25)
+    torch.manual_seed(11)
+    y1 = m(xg).detach()
+    torch.manual_seed(11)
+    y2 = m(xg).detach()
+    torch.manual_seed(12)
+    y3 = m(xg).detach()
+    assert torch.equal(y1, y2), "same torch seed -> same dropout masks"
+    assert not torch.equal(y1, y3), "different seed -> different masks"
+    m0 = _build(meta, sd, cuda_device, "bf16x3", dropout=0.0)
+    y0 = m0(xg).detach()
+    assert torch.isfinite(y1).all()
+    # dropout perturbs but does not bias the activations grossly
+    assert float((y1 - y0).abs().mean()) > 1e-3
+    assert float(y1.abs().mean()) < 3 * float(y0.abs().mean()) + 1.0
+
+
+def test_directional_finite_difference_with_dropout(cuda_device):
+    """d/de loss(w + e*d) at e = 0 equals <grad, d> with the dropout masks frozen by the seed."""
+    meta, sd, x, _, new = load_golden("opt_333_c128_train")
+    xg = x.to(cuda_device)
+    gy = torch.from_numpy(new["gy"]).to(cuda_device)
+    m = _build(meta, sd, cuda_device, "bf16x3", dropout=0.25)
+
+    def loss():
+        torch.manual_seed(21)
+        return (m(xg) * gy).sum()
+
+    l0 = loss()
+    l0.backward()
+    g = torch.Generator().manual_seed(3)
+    names = ["layers_conv.1.weight", "layers_bn.0.weight", "expand_conv.weight", "shrink.bias",
+             "layers_conv.2.weight", "layers_bn.3.bias"]
+    prm = dict(m.named_parameters())
+    for k in names:
+        d = torch.randn(prm[k].shape, generator=g).to(cuda_device)
+        d = d / d.norm() * prm[k].detach().norm() * 1e-2
+        analytic = float((prm[k].grad * d).sum())
+        with torch.no_grad():
+            prm[k].add_(d)
+            lp = float(loss())
+            prm[k].sub_(2 * d)
+            lm = float(loss())
+            prm[k].add_(d)
+        numeric = (lp - lm) / 2
+        assert abs(numeric - analytic) <= 0.05 * max(abs(analytic), abs(numeric)) + 1e-3, \
+            (k, numeric, analytic)
+
+
+def test_cfg3_full_size_train_step(cuda_device):
+    """BASELINE configs[2] shape: arc 3^5, N = 1024, T = 243, fwd + bwd + AMSGrad step: finite,
+    loss decreases over a few steps on a fixed batch."""
+    from oracle import temporal_model_oracle as orc
+    arc = [3, 3, 3, 3, 3]
+    sd = orc.make_state_dict(17, 2, 17, arc, 1024, seed=0)
+    m = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=arc, dropout=0.25, channels=1024)
+    m.load_state_dict(sd)
+    m = m.to(cuda_device).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
+    x = orc.make_input(1024, 243, seed=5).to(cuda_device)
+    tgt = torch.randn(1024, 1, 17, 3, generator=torch.Generator().manual_seed(6)).to(cuda_device) * 0.3
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = orc.mpjpe(m(x), tgt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+
+
+def test_temporal_model_train_raises_not_silently_falls_back(cuda_device):
+    m = vp.TemporalModel(17, 2, 17, [3, 3, 3], channels=64).to(cuda_device).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(2, 27, 17, 2, device=cuda_device))

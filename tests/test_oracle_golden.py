@@ -32,6 +32,8 @@ def test_numpy_restatement_matches_reference(name):
     assert _rel(y, y_ref) < 2e-5
     if train:
         for k, v in new.items():
+            if k == "gy" or k.startswith("grad/"):
+                continue
             if k.endswith("num_batches_tracked"):
                 assert int(res[1][k]) == int(v)
             else:
@@ -46,16 +48,26 @@ def test_torch_restatement_matches_reference(name):
     strided = meta["cls"] == "TemporalModelOptimized1f"
     train = bool(meta.get("train"))
     sd = {k: v.clone() for k, v in sd.items()}
-    with torch.no_grad():
+    if train:
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and "running" not in k:
+                v.requires_grad_(True)
+    with torch.set_grad_enabled(train):
         y = orc.forward_torch(sd, x, meta["fw"], causal=meta["causal"], dense=meta["dense"],
                               strided=strided, training=train, momentum=meta.get("momentum", 0.1),
                               update_stats=train)
     assert tuple(y.shape) == y_ref.shape
-    assert _rel(y.numpy(), y_ref) < 2e-5
+    assert _rel(y.detach().numpy(), y_ref) < 2e-5
     if train:
+        (y * torch.from_numpy(new["gy"])).sum().backward()
         for k, v in new.items():
-            if not k.endswith("num_batches_tracked"):
-                assert _rel(sd[k].numpy(), v) < 2e-5, k
+            if k == "gy" or k.endswith("num_batches_tracked"):
+                continue
+            if k.startswith("grad/"):
+                # the oracle's autograd gradients == the reference's (both fp32 on CPU)
+                assert _rel(sd[k[5:]].grad.numpy(), v) < 1e-4, k
+            else:
+                assert _rel(sd[k].detach().numpy(), v) < 2e-5, k
 
 
 def test_eval_cone_equals_dilated():

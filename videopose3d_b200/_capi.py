@@ -15,8 +15,10 @@ VP3D_VARIANT_DILATED = 0
 VP3D_VARIANT_STRIDED = 1
 VP3D_PRECISION_BF16 = 0
 VP3D_PRECISION_BF16X3 = 1
+VP3D_PRECISION_MIXED = 2
 VP3D_PACK_CONV = 1
 VP3D_PACK_BN_EVAL = 2
+VP3D_PACK_CONV_T = 4
 
 _LIB_NAME = "libvp3d_b200.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", _LIB_NAME)
@@ -50,6 +52,17 @@ class Weights(ctypes.Structure):
     ]
 
 
+class Grads(ctypes.Structure):
+    _fields_ = [
+        ("expand_conv_weight", ctypes.c_void_p),
+        ("expand_bn", ctypes.c_void_p * 2),
+        ("layers_conv_weight", ctypes.c_void_p * VP3D_MAX_LAYERS),
+        ("layers_bn", (ctypes.c_void_p * 2) * VP3D_MAX_LAYERS),
+        ("shrink_weight", ctypes.c_void_p),
+        ("shrink_bias", ctypes.c_void_p),
+    ]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [
         ("a", ctypes.c_void_p),
@@ -77,6 +90,9 @@ class ConvDesc(ctypes.Structure):
         ("res_row_step", ctypes.c_int),
         ("res_row_off", ctypes.c_int),
         ("res_sample_div", ctypes.c_int),
+        ("res_col_begin", ctypes.c_int),
+        ("res_cols", ctypes.c_int),
+        ("res_check_rows", ctypes.c_int),
         ("out", ctypes.c_void_p),
         ("out_planes", ctypes.c_int),
         ("out_plane_stride", ctypes.c_longlong),
@@ -105,6 +121,14 @@ SIGNATURES = {
                                          ctypes.c_size_t, ctypes.c_void_p]),
     "vp3d_forward_eval_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int, ctypes.c_int]),
+    "vp3d_train_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "vp3d_forward_train": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.POINTER(Weights),
+                                          ctypes.POINTER(ctypes.c_float), ctypes.c_float,
+                                          ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_size_t,
+                                          ctypes.c_void_p]),
+    "vp3d_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Grads),
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "vp3d_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "vp3d_profile_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "vp3d_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),

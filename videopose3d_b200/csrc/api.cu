@@ -9,33 +9,22 @@
 #include <string>
 #include <vector>
 
-#include "../../include/vp3d_b200.h"
-#include "conv_gemm.cuh"
+#include "internal.cuh"
 #include "pack.cuh"
 
 using namespace vp3d;
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
+namespace vp3d {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-#define CUDA_TRY(expr)                                                                     \
-  do {                                                                                     \
-    cudaError_t _e = (expr);                                                               \
-    if (_e != cudaSuccess)                                                                 \
-      return fail(VP3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
-                  __FILE__, __LINE__);                                                     \
-  } while (0)
-#define VP3D_TRY(expr)          \
-  do {                          \
-    int _s = (expr);            \
-    if (_s != VP3D_OK) return _s; \
-  } while (0)
+}  // namespace vp3d
 
 // ------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -56,7 +45,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 4-D bf16 map (k, row, sample, plane), box (64, box_rows, 1, 1), 128-byte swizzle.
-static int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+namespace vp3d {
+int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
                        uint64_t row_stride, uint64_t samples, uint64_t sample_stride,
                        uint64_t planes, uint64_t plane_stride, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -83,7 +73,7 @@ static int make_map_4d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 }
 
 // 2-D bf16 map (k, row), box (64, box_rows), 128-byte swizzle.
-static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
+int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows,
                        uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -100,16 +90,14 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
   return VP3D_OK;
 }
 
-static int pick_block_n(int n_pad) {
+int pick_block_n(int n_pad) {
   if (n_pad % 256 == 0) return 256;
   if (n_pad % 128 == 0) return 128;
   return 64;
 }
-static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -120,7 +108,7 @@ static int num_sms() {
 }
 
 // ------------------------------------------------------------------ operator level
-static int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
+int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   if (!d || !d->a || !d->w) return fail(VP3D_ERR_INVALID, "conv_gemm: null operand");
   if (d->a_ld % 64 || d->k_per_tap % 64 || d->n_pad % 64)
     return fail(VP3D_ERR_INVALID, "conv_gemm: a_ld, k_per_tap and n_pad must be multiples of 64");
@@ -132,7 +120,22 @@ static int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   if (pairs == 3 && a_planes != 2)
     return fail(VP3D_ERR_INVALID, "conv_gemm: bf16x3 needs hi/lo planes of A");
   const int w_planes = pairs == 3 ? 2 : 1;
-  const int block_n = pick_block_n(d->n_pad);
+  // Largest N tile that still yields at least one tile per SM; small layers (few row tiles) fall
+  // back to narrower tiles so that more SMs (and more TMEM/TMA pipelines) share the work.
+  int block_n = 64;
+  {
+    const long long rows_total = d->per_sample_tiles ? 0 : d->out_rows;
+    const long long m_tiles = d->per_sample_tiles
+                                  ? (long long)d->samples * ((d->out_rows + kBlockM - 1) / kBlockM)
+                                  : (rows_total + kBlockM - 1) / kBlockM;
+    const int cands[3] = {256, 128, 64};
+    bool found = false;
+    for (int c : cands) {
+      if (d->n_pad % c) continue;
+      if (m_tiles * (d->n_pad / c) >= num_sms()) { block_n = c; found = true; break; }
+    }
+    if (!found) block_n = 64;
+  }
 
   CUtensorMap ma, mw;
   const uint64_t a_rows = d->a_rows, a_ld = d->a_ld;
@@ -170,6 +173,9 @@ static int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   g.res_row_step = d->res_row_step;
   g.res_row_off = d->res_row_off;
   g.res_sample_div = d->res_sample_div;
+  g.res_col_begin = d->res_col_begin;
+  g.res_cols = d->res_cols > 0 ? d->res_cols : d->n_pad;
+  g.res_check_rows = d->res_check_rows;
   g.out = static_cast<__nv_bfloat16*>(d->out);
   g.out_plane_stride = d->out_plane_stride;
   g.out_planes = d->out_planes > 0 ? d->out_planes : 1;
@@ -186,50 +192,15 @@ static int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------ plan
-struct PackedConv {
-  __nv_bfloat16* w = nullptr;
-  int taps = 0;       // taps as stored (1 when merged)
-  int k_per_tap = 0;  // padded
-  int n_pad = 0;
-  int merged = 0;
-  float* scale = nullptr;  // eval affine [n_pad]
-  float* shift = nullptr;
-};
-
-struct vp3d_plan {
-  vp3d_config cfg;
-  int nb = 0;  // residual blocks
-  int C = 0, c_in_raw = 0, c_out_raw = 0, c_in_pad = 0, k0_pad = 0, c_out_pad = 0;
-  int planes = 1;
-  int pad[VP3D_MAX_WIDTHS];
-  int shift_dil[VP3D_MAX_WIDTHS];  // causal shift in frames (TemporalModel, model.py:111)
-  int shift_str[VP3D_MAX_WIDTHS];  // causal shift in strided units (Optimized1f, model.py:176)
-  int dilation[VP3D_MAX_WIDTHS];
-  int taps[VP3D_MAX_WIDTHS];       // taps of block i's first conv (dense: 2*pad+1)
-  PackedConv expand_dil, expand_flat, shrink;
-  PackedConv conv[VP3D_MAX_LAYERS];
-  std::vector<void*> allocs;
-  bool conv_packed = false, bn_packed = false;
-  // host-API staging (owned)
-  float* d_x = nullptr;
-  float* d_y = nullptr;
-  void* d_ws = nullptr;
-  size_t d_x_bytes = 0, d_y_bytes = 0, d_ws_bytes = 0;
-  cudaStream_t stream = nullptr;
-  int last_launches = 0;
-  // measurement hook: event pairs around one chosen launch of each forward
-  int prof_launch = -1;
-  std::vector<cudaEvent_t> prof_events;  // start/stop pairs
-  size_t prof_used = 0;                  // events consumed since the last read
-};
-
-static int plan_alloc(vp3d_plan* p, void** out, size_t bytes) {
+int plan_alloc(vp3d_plan* p, void** out, size_t bytes) {
   void* q = nullptr;
   CUDA_TRY(cudaMalloc(&q, bytes));
   p->allocs.push_back(q);
   *out = q;
   return VP3D_OK;
 }
+
+}  // namespace vp3d
 
 static int alloc_packed(vp3d_plan* p, PackedConv& pc, int taps, int k_per_tap, int n_pad,
                         int merged) {
@@ -258,6 +229,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
   if (cfg->channels < 64 || cfg->channels % 64)
     return fail(VP3D_ERR_UNSUPPORTED, "channels must be a positive multiple of 64 (got %d)",
                 cfg->channels);
+  if (cfg->precision < VP3D_PRECISION_BF16 || cfg->precision > VP3D_PRECISION_MIXED)
+    return fail(VP3D_ERR_INVALID, "plan_create: unknown precision %d", cfg->precision);
   if (cfg->variant != VP3D_VARIANT_DILATED && cfg->variant != VP3D_VARIANT_STRIDED)
     return fail(VP3D_ERR_INVALID, "plan_create: unknown variant %d", cfg->variant);
   if (cfg->variant == VP3D_VARIANT_STRIDED && cfg->dense)
@@ -275,7 +248,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
   p->c_in_pad = round_up(p->c_in_raw, 64);
   p->k0_pad = round_up(p->c_in_raw * cfg->filter_widths[0], 64);
   p->c_out_pad = round_up(p->c_out_raw, 64);
-  p->planes = cfg->precision == VP3D_PRECISION_BF16X3 ? 2 : 1;
+  p->planes = cfg->precision == VP3D_PRECISION_BF16 ? 1 : 2;
   // model.py:31, 107-121 / :172-184
   p->pad[0] = cfg->filter_widths[0] / 2;
   p->shift_dil[0] = p->shift_str[0] = cfg->causal ? cfg->filter_widths[0] / 2 : 0;
@@ -331,6 +304,7 @@ extern "C" __attribute__((visibility("default"))) void vp3d_plan_destroy(vp3d_pl
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->stream) cudaStreamDestroy(p->stream);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  if (p->train) train_state_destroy(p->train);
   delete p;
 }
 
@@ -394,6 +368,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
                                 p->c_out_pad, stream));
     p->bn_packed = true;
   }
+  if (what & VP3D_PACK_CONV_T) VP3D_TRY(train_pack_transposed(p, w, stream));
   return VP3D_OK;
 }
 
@@ -402,13 +377,14 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
 // mode when the input is exactly one receptive field long: with running statistics every output
 // frame depends only on its own dependency cone, whose rows are exactly the stride-w rows
 // Optimized1f computes (the reference states the weights are interchangeable, model.py:146-148).
-static bool use_strided(const vp3d_plan* p, int T) {
+namespace vp3d {
+bool use_strided(const vp3d_plan* p, int T) {
   if (p->cfg.variant == VP3D_VARIANT_STRIDED) return true;
   return !p->cfg.dense && T == vp3d_receptive_field(p);
 }
 
 // rows per sample after each stage: L[0] = rows out of expand, L[i] = rows out of block i
-static int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
+int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
   const int* fw = p->cfg.filter_widths;
   if (strided) {
     L[0] = T / fw[0];  // Conv1d(stride=w, kernel=w): floor((T - w)/w) + 1
@@ -421,6 +397,8 @@ static int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
     if (L[i] < 1) return 0;
   return L[p->nb];
 }
+
+}  // namespace vp3d
 
 extern "C" __attribute__((visibility("default"))) int vp3d_output_frames(const vp3d_plan* p, int T) {
   if (!p) return fail(VP3D_ERR_INVALID, "null plan");
@@ -501,11 +479,31 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     ++launches;                    \
   } while (0)
 
+  // Per-layer operand precision.  index 0 = expand, 1..nb = residual blocks, nb+1 = shrink.
+  //   bf16   : every GEMM single-plane bf16.
+  //   bf16x3 : every GEMM split-bf16 (3 MMAs per product).
+  //   mixed  : the residual stream X keeps hi+lo planes (skip path exact); GEMMs holding < 8% of
+  //            the forward FLOPs (expand, shrink, the narrow tail blocks) run split-bf16, the
+  //            FLOP-dominant blocks run plain bf16 on the hi plane.
+  bool x3[VP3D_MAX_WIDTHS + 1];
+  {
+    double fl[VP3D_MAX_WIDTHS + 1], total = 0.0;
+    fl[0] = (double)N * L[0] * p->c_in_raw * fw[0] * C;
+    for (int i = 1; i <= p->nb; ++i) fl[i] = (double)N * L[i] * (p->taps[i] + 1.0) * C * C;
+    fl[p->nb + 1] = (double)N * L[p->nb] * C * p->c_out_raw;
+    for (int i = 0; i <= p->nb + 1; ++i) total += fl[i];
+    for (int i = 0; i <= p->nb + 1; ++i) {
+      if (p->cfg.precision == VP3D_PRECISION_BF16) x3[i] = false;
+      else if (p->cfg.precision == VP3D_PRECISION_BF16X3) x3[i] = true;
+      else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.08 * total);
+    }
+  }
+
   vp3d_conv_desc d;
-  auto common = [&](vp3d_conv_desc& q) {
+  auto common = [&](vp3d_conv_desc& q, bool layer_x3) {
     memset(&q, 0, sizeof(q));
     q.a_planes = p->planes;
-    q.precision = p->cfg.precision;
+    q.precision = layer_x3 ? VP3D_PRECISION_BF16X3 : VP3D_PRECISION_BF16;
     q.out_planes = p->planes;
     q.res_planes = p->planes;
   };
@@ -514,14 +512,14 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   if (strided) {
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
                                (long long)wl.a0_plane, stream)));
-    common(d);
+    common(d, x3[0]);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
     d.per_sample_tiles = 0; d.out_rows = N * L[0];
   } else {
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
                                (long long)wl.a0_plane, stream)));
-    common(d);
+    common(d, x3[0]);
     d.a = a0; d.samples = N; d.a_rows = T; d.a_ld = p->c_in_pad;
     d.w = p->expand_dil.w; d.taps = fw[0]; d.k_per_tap = p->c_in_pad; d.n_pad = C;
     d.per_sample_tiles = 1; d.tap_row_step = 1; d.out_rows = L[0];
@@ -539,7 +537,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     const int Lin = L[i - 1], Lout = L[i];
     const size_t h_plane = (size_t)N * Lout * C;
     // first conv of the block: dilated / strided k-tap conv + BN + ReLU
-    common(d);
+    common(d, x3[i]);
+    d.out_planes = x3[i] ? 2 : 1;  // H only needs a lo plane when its consumer is split-bf16
     d.a = xb[cur];
     d.w = c0.w; d.taps = c0.taps; d.k_per_tap = C; d.n_pad = C;
     d.scale = c0.scale; d.shift = c0.shift; d.relu = 1;
@@ -568,7 +567,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
 
     // second conv: 1x1 + BN + ReLU + sliced residual
-    common(d);
+    common(d, x3[i]);
+    d.a_planes = x3[i] ? 2 : 1;
     d.a = hb; d.samples = 1; d.a_rows = N * Lout; d.a_ld = C;
     d.w = c1.w; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
     d.per_sample_tiles = 0; d.out_rows = N * Lout;
@@ -588,7 +588,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   }
 
   // ---- shrink (model.py:137 / :196) writing (N, T_out, J_out, 3) directly (fuses :74-75)
-  common(d);
+  common(d, x3[p->nb + 1]);
   d.a = xb[cur]; d.samples = 1; d.a_rows = N * L[p->nb]; d.a_ld = C;
   d.w = p->shrink.w; d.taps = 1; d.k_per_tap = C; d.n_pad = p->c_out_pad;
   d.per_sample_tiles = 0; d.out_rows = N * L[p->nb];

@@ -159,14 +159,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool valid = t < p.out_rows;
       const long long out_row = (long long)sample * p.out_rows + t;
       long long res_row;
-      if (!p.dilated && p.res_sample_div > 0) {
-        const int rs = t / p.res_sample_div;
-        const int rt = t - rs * p.res_sample_div;
-        res_row = (long long)rs * p.res_rows_per_sample + (long long)rt * p.res_row_step +
-                  p.res_row_off;
-      } else {
-        res_row = (long long)sample * p.res_rows_per_sample + (long long)t * p.res_row_step +
-                  p.res_row_off;
+      bool res_ok = valid;
+      {
+        int rs = sample, rt = t;
+        if (!p.dilated && p.res_sample_div > 0) {
+          rs = t / p.res_sample_div;
+          rt = t - rs * p.res_sample_div;
+        }
+        const long long in_sample = (long long)rt * p.res_row_step + p.res_row_off;
+        if (p.res_check_rows && (in_sample < 0 || in_sample >= p.res_rows_per_sample)) res_ok = false;
+        res_row = (long long)rs * p.res_rows_per_sample + in_sample;
       }
 
       mbar_wait(tfull_bar + acc * 8, acc_phase);
@@ -198,8 +200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-        if (do_res && valid) {
-          const __nv_bfloat16* rp = p.res + res_row * p.res_ld + c0;
+        if (do_res && res_ok && c0 >= p.res_col_begin && c0 < p.res_col_begin + p.res_cols) {
+          const __nv_bfloat16* rp = p.res + res_row * p.res_ld + (c0 - p.res_col_begin);
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) {
             if (pl < p.res_planes) {

@@ -61,6 +61,9 @@ struct ConvGemmArgs {
   int res_row_step;            // residual row = sample*res_rows_per_sample + t*res_row_step + res_row_off
   int res_row_off;
   int res_sample_div;           // flat tiling: split row -> (row / div, row % div) for the residual map; 0 = off
+  int res_col_begin;            // residual is added only to output columns [res_col_begin, +res_cols)
+  int res_cols;                 //   reading residual column (col - res_col_begin)   (dgrad skip path)
+  int res_check_rows;           // 1: skip rows whose mapped in-sample row falls outside [0, res_rows_per_sample)
   __nv_bfloat16* out;          // bf16 output plane 0, [samples*out_rows, out_ld]
   long long out_plane_stride;
   int out_planes;              // 1 or 2

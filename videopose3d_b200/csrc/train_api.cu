@@ -1,0 +1,440 @@
+// Training-mode forward and backward (C ABI): vp3d_forward_train / vp3d_backward.
+//
+// Forward, per conv layer (model.py:127,134-135 / :188,193-194 in train() mode):
+//   Z  = conv(X_prev)                 tcgen05 GEMM, raw bf16 store + per-channel sum / sumsq epilogue
+//   (scale, shift, mean, invstd)      bn_finalize (+ running_mean / running_var update, momentum
+//                                     read from the caller at call time, model.py:36-39)
+//   X  = dropout(relu(Z*scale+shift)) [+ residual slice]   bn_apply (bandwidth pass)
+// Saved for backward: the packed input, every Z and every X/H (bf16 planes) + the BN vectors.
+//
+// Backward, per layer top-down: BN/ReLU/Dropout backward (bn_bwd_reduce + bn_bwd_apply -> dZ,
+// dgamma, dbeta), weight gradient dW = dZ^T * X (MN-major tcgen05 GEMM, split over rows),
+// data gradient G_prev = dZ * W^T through the same conv GEMM kernel on transposed weight packs,
+// with the skip-connection gradient added in the epilogue.
+//
+// Covered schedule: the strided layout (TemporalModelOptimized1f, the model run.py trains with by
+// default, run.py:172-175).  Training the dilated TemporalModel returns VP3D_ERR_UNSUPPORTED.
+#include <stdio.h>
+
+#include "internal.cuh"
+#include "pack.cuh"
+#include "train_ops.cuh"
+#include "wgrad_gemm.cuh"
+
+namespace vp3d {
+
+struct TrainState {
+  __nv_bfloat16* conv_t[VP3D_MAX_LAYERS] = {};  // [planes][taps][C][C], out[tap][ci][co]
+  __nv_bfloat16* shrink_t = nullptr;            // [planes][1][C][c_out_pad128]
+  bool packed_t = false;
+  float* vec = nullptr;       // per BN layer l: scale, shift, mean, invstd, stats[2C], sums[2C]
+  size_t vec_floats = 0;
+  float* shrink_affine = nullptr;  // scale / shift of the shrink bias [2 * c_out_pad]
+  // configuration of the last forward (needed by backward)
+  int N = 0, T = 0;
+  int L[VP3D_MAX_WIDTHS] = {};
+  float dropout_p = 0.0f;
+  uint64_t seed = 0;
+  bool have_forward = false;
+  std::vector<void*> allocs;
+};
+
+void train_state_destroy(TrainState* t) {
+  if (!t) return;
+  for (void* q : t->allocs) cudaFree(q);
+  delete t;
+}
+
+namespace {
+
+int t_alloc(TrainState* t, void** out, size_t bytes) {
+  void* q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, bytes));
+  t->allocs.push_back(q);
+  *out = q;
+  return VP3D_OK;
+}
+
+int c_out_pad128(const vp3d_plan* p) { return round_up(p->c_out_raw, 128); }
+
+int ensure_train_state(vp3d_plan* p) {
+  if (p->train) return VP3D_OK;
+  TrainState* t = new TrainState();
+  p->train = t;
+  const size_t cc = (size_t)p->C * p->C;
+  for (int i = 0; i < p->nb; ++i) {
+    VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->conv_t[2 * i]),
+                     (size_t)p->planes * p->taps[i + 1] * cc * 2));
+    VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->conv_t[2 * i + 1]), (size_t)p->planes * cc * 2));
+  }
+  VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->shrink_t),
+                   (size_t)p->planes * p->C * c_out_pad128(p) * 2));
+  t->vec_floats = (size_t)(2 * p->nb + 1) * 8 * p->C;
+  VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->vec), t->vec_floats * sizeof(float)));
+  VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->shrink_affine), 2 * p->c_out_pad * sizeof(float)));
+  return VP3D_OK;
+}
+
+struct LayerVec {
+  float *scale, *shift, *mean, *invstd, *stats, *sums;
+};
+LayerVec layer_vec(const vp3d_plan* p, int l) {
+  float* b = p->train->vec + (size_t)l * 8 * p->C;
+  return {b, b + p->C, b + 2 * p->C, b + 3 * p->C, b + 4 * p->C, b + 6 * p->C};
+}
+
+// ---------------------------------------------------------------- workspace layout (strided)
+struct TrainLayout {
+  size_t a0 = 0;
+  size_t z[VP3D_MAX_LAYERS + 1] = {};   // pre-BN conv outputs, layer 0 = expand
+  size_t x[VP3D_MAX_WIDTHS] = {};       // x[0] = expand output, x[i] = output of block i
+  size_t h[VP3D_MAX_WIDTHS] = {};       // h[i] = output of the first conv (post act) of block i
+  size_t g0 = 0, g1 = 0, dz = 0, dyp = 0, partial = 0;
+  size_t partial_bytes = 0;
+  size_t total = 0;
+  long long rows[VP3D_MAX_WIDTHS] = {};  // rows[i] = N * L[i]
+};
+
+TrainLayout train_layout(const vp3d_plan* p, int N, const int* L) {
+  TrainLayout w;
+  const size_t C = p->C, pl = p->planes;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  for (int i = 0; i <= p->nb; ++i) w.rows[i] = (long long)N * L[i];
+  w.a0 = take(pl * w.rows[0] * p->k0_pad * 2);
+  w.z[0] = take(pl * w.rows[0] * C * 2);
+  w.x[0] = take(pl * w.rows[0] * C * 2);
+  for (int i = 1; i <= p->nb; ++i) {
+    const size_t b = pl * w.rows[i] * C * 2;
+    w.z[2 * i - 1] = take(b);
+    w.h[i] = take(b);
+    w.z[2 * i] = take(b);
+    w.x[i] = take(b);
+  }
+  const size_t big = pl * w.rows[0] * C * 2;
+  w.g0 = take(big);
+  w.g1 = take(big);
+  w.dz = take(big);
+  w.dyp = take(pl * w.rows[p->nb] * c_out_pad128(p) * 2);
+  // wgrad partials: up to 8 splits x taps x C x max(C, k0_pad) fp32
+  int max_taps = 1;
+  for (int i = 1; i <= p->nb; ++i) max_taps = p->taps[i] > max_taps ? p->taps[i] : max_taps;
+  const size_t n_max = p->C > p->k0_pad ? p->C : p->k0_pad;
+  w.partial_bytes = (size_t)8 * max_taps * round_up(p->C, 128) * round_up((int)n_max, 64) * 4;
+  w.partial = take(w.partial_bytes);
+  w.total = off + 1024;
+  return w;
+}
+
+// dW = dZ^T X for one conv layer.  dz: [planes][rows][dz_ld]; x: [planes][rows][x_ld].
+int run_wgrad(const vp3d_plan* p, const __nv_bfloat16* dz, int dz_ld, const __nv_bfloat16* x,
+              int x_ld, long long rows, int taps, int tap_col_step, int c_out, int c_in_cols,
+              int c_in, int taps_out, int merged, float* grad, float* partial, size_t partial_bytes,
+              cudaStream_t stream) {
+  const int block_n = pick_block_n(round_up(c_in_cols, 64));
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.per_sample = 0;
+  a.samples = 1;
+  a.rows = (int)rows;
+  a.kchunks = (int)((rows + 63) / 64);
+  a.taps = taps;
+  a.tap_row_step = 0;
+  a.tap_col_step = tap_col_step;
+  a.m_pad = round_up(c_out, 128);
+  a.n_pad = round_up(c_in_cols, block_n);
+  a.m_tiles = a.m_pad / 128;
+  a.n_tiles = a.n_pad / block_n;
+  a.pairs = p->planes == 2 ? 3 : 1;
+  const int items = taps * a.m_tiles * a.n_tiles;
+  int splits = (2 * num_sms() + items - 1) / items;
+  if (splits > 8) splits = 8;
+  if (splits > a.kchunks) splits = a.kchunks;
+  if (splits < 1) splits = 1;
+  while ((size_t)splits * taps * a.m_pad * a.n_pad * 4 > partial_bytes && splits > 1) --splits;
+  if ((size_t)splits * taps * a.m_pad * a.n_pad * 4 > partial_bytes)
+    return fail(VP3D_ERR_WORKSPACE, "wgrad partial buffer too small");
+  a.splits = splits;
+  a.partial = partial;
+  CUtensorMap mdz, mx;
+  VP3D_TRY(make_map_4d(&mdz, dz, dz_ld, rows, dz_ld, 1, (uint64_t)rows * dz_ld, p->planes,
+                       (uint64_t)rows * dz_ld, 64));
+  VP3D_TRY(make_map_4d(&mx, x, x_ld, rows, x_ld, 1, (uint64_t)rows * x_ld, p->planes,
+                       (uint64_t)rows * x_ld, 64));
+  CUDA_TRY(launch_wgrad_gemm(mdz, mx, a, block_n, num_sms(), stream));
+  CUDA_TRY(launch_wgrad_reduce(partial, grad, splits, taps, a.m_pad, a.n_pad, c_out, c_in, taps_out,
+                               merged, stream));
+  return VP3D_OK;
+}
+
+DropoutCfg drop_cfg(const TrainState* t, int layer) {
+  DropoutCfg d;
+  d.p = t->dropout_p;
+  d.seed_lo = (uint32_t)(t->seed & 0xFFFFFFFFu);
+  d.seed_hi = (uint32_t)(t->seed >> 32);
+  d.layer = (uint32_t)layer;
+  return d;
+}
+
+}  // namespace
+
+int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream) {
+  VP3D_TRY(ensure_train_state(p));
+  TrainState* t = p->train;
+  for (int i = 0; i < p->nb; ++i) {
+    CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i], t->conv_t[2 * i], p->planes,
+                                       p->C, p->C, p->taps[i + 1], p->C, p->C, stream));
+    CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i + 1], t->conv_t[2 * i + 1],
+                                       p->planes, p->C, p->C, 1, p->C, p->C, stream));
+  }
+  CUDA_TRY(launch_pack_conv_weight_t(w->shrink_weight, t->shrink_t, p->planes, p->c_out_raw, p->C, 1,
+                                     p->C, c_out_pad128(p), stream));
+  t->packed_t = true;
+  return VP3D_OK;
+}
+
+}  // namespace vp3d
+
+using namespace vp3d;
+
+#define VP3D_API extern "C" __attribute__((visibility("default")))
+
+VP3D_API size_t vp3d_train_workspace_bytes(const vp3d_plan* p, int N, int T) {
+  if (!p || N < 1) return 0;
+  int L[VP3D_MAX_WIDTHS];
+  if (!layer_rows(p, T, true, L)) return 0;
+  return train_layout(p, N, L).total;
+}
+
+VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, int T,
+                                const vp3d_weights* w, const float* bn_momentum, float dropout_p,
+                                unsigned long long seed, void* ws, size_t ws_bytes, void* stream_) {
+  if (!p || !x || !y || !w || !bn_momentum)
+    return fail(VP3D_ERR_INVALID, "forward_train: null argument");
+  if (p->cfg.variant != VP3D_VARIANT_STRIDED)
+    return fail(VP3D_ERR_UNSUPPORTED,
+                "training kernels cover TemporalModelOptimized1f (strided) only; TemporalModel in "
+                "train() mode is not built yet");
+  if (N < 1) return fail(VP3D_ERR_INVALID, "forward_train: batch must be >= 1");
+  if (dropout_p < 0.0f || dropout_p >= 1.0f)
+    return fail(VP3D_ERR_INVALID, "forward_train: dropout p must be in [0, 1)");
+  if (!p->conv_packed) return fail(VP3D_ERR_STATE, "forward_train: conv weights not packed");
+  VP3D_TRY(ensure_train_state(p));
+  TrainState* t = p->train;
+  if (!t->packed_t) return fail(VP3D_ERR_STATE, "forward_train: transposed weights not packed");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int L[VP3D_MAX_WIDTHS];
+  if (!layer_rows(p, T, true, L))
+    return fail(VP3D_ERR_INVALID, "forward_train: sequence of %d frames is too short", T);
+  const int* fw = p->cfg.filter_widths;
+  for (int i = 1; i <= p->nb; ++i)
+    if (L[i - 1] != fw[i] * L[i])
+      return fail(VP3D_ERR_UNSUPPORTED, "strided training needs layer lengths divisible by the "
+                  "filter width (block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
+  const TrainLayout wl = train_layout(p, N, L);
+  if (!ws || ws_bytes < wl.total)
+    return fail(VP3D_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes, wl.total);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
+  const int C = p->C, pl = p->planes;
+  t->N = N; t->T = T; t->dropout_p = dropout_p; t->seed = seed; t->have_forward = false;
+  for (int i = 0; i <= p->nb; ++i) t->L[i] = L[i];
+  int launches = 0;
+
+  CUDA_TRY(cudaMemsetAsync(t->vec, 0, t->vec_floats * sizeof(float), stream));
+  CUDA_TRY(launch_bias_affine(w->shrink_bias, t->shrink_affine, t->shrink_affine + p->c_out_pad,
+                              p->c_out_raw, p->c_out_pad, stream));
+  ++launches;
+
+  vp3d_conv_desc d;
+  auto common = [&](vp3d_conv_desc& q) {
+    memset(&q, 0, sizeof(q));
+    q.a_planes = pl;
+    q.precision = p->cfg.precision;
+    q.out_planes = pl;
+    q.samples = 1;
+    q.per_sample_tiles = 0;
+  };
+  auto bn = [&](int layer, const float* const* bnp, long long rows, const __nv_bfloat16* z,
+                __nv_bfloat16* out, const __nv_bfloat16* res, long long res_plane, RowMap map) -> int {
+    const LayerVec v = layer_vec(p, layer);
+    CUDA_TRY(launch_bn_finalize(v.stats, rows, bnp[0], bnp[1], const_cast<float*>(bnp[2]),
+                                const_cast<float*>(bnp[3]), bn_momentum[layer], 1e-5f, v.scale,
+                                v.shift, v.mean, v.invstd, C, stream));
+    CUDA_TRY(launch_bn_apply(z, rows * C, out, rows * C, pl, rows, C, v.scale, v.shift,
+                             drop_cfg(t, layer), res, res_plane, map, stream));
+    launches += 2;
+    return VP3D_OK;
+  };
+  const RowMap no_map = {0, 0, 1, 0};
+
+  // ---- expand (model.py:188)
+  CUDA_TRY(launch_pack_input(x, bf(wl.a0), pl, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
+                             wl.rows[0] * p->k0_pad, stream));
+  ++launches;
+  common(d);
+  d.a = bf(wl.a0); d.a_rows = (int)wl.rows[0]; d.a_ld = p->k0_pad;
+  d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
+  d.out_rows = (int)wl.rows[0];
+  d.out = bf(wl.z[0]); d.out_plane_stride = wl.rows[0] * C; d.out_ld = C;
+  d.stats = layer_vec(p, 0).stats;
+  VP3D_TRY(run_conv(&d, stream));
+  ++launches;
+  VP3D_TRY(bn(0, w->expand_bn, wl.rows[0], bf(wl.z[0]), bf(wl.x[0]), nullptr, 0, no_map));
+
+  // ---- residual blocks (model.py:190-194)
+  for (int i = 1; i <= p->nb; ++i) {
+    const long long rows = wl.rows[i];
+    const int l1 = 2 * i - 1, l2 = 2 * i;
+    common(d);
+    d.a = bf(wl.x[i - 1]); d.a_rows = (int)rows; d.a_ld = fw[i] * C;
+    d.w = p->conv[2 * (i - 1)].w; d.taps = p->taps[i]; d.k_per_tap = C; d.n_pad = C;
+    d.tap_col_step = C; d.out_rows = (int)rows;
+    d.out = bf(wl.z[l1]); d.out_plane_stride = rows * C; d.out_ld = C;
+    d.stats = layer_vec(p, l1).stats;
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+    VP3D_TRY(bn(l1, w->layers_bn[2 * (i - 1)], rows, bf(wl.z[l1]), bf(wl.h[i]), nullptr, 0, no_map));
+
+    common(d);
+    d.a = bf(wl.h[i]); d.a_rows = (int)rows; d.a_ld = C;
+    d.w = p->conv[2 * (i - 1) + 1].w; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
+    d.out_rows = (int)rows;
+    d.out = bf(wl.z[l2]); d.out_plane_stride = rows * C; d.out_ld = C;
+    d.stats = layer_vec(p, l2).stats;
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+    const RowMap rm = {0, 0, fw[i], fw[i] / 2 + p->shift_str[i]};
+    VP3D_TRY(bn(l2, w->layers_bn[2 * (i - 1) + 1], rows, bf(wl.z[l2]), bf(wl.x[i]), bf(wl.x[i - 1]),
+                wl.rows[i - 1] * C, rm));
+  }
+
+  // ---- shrink (model.py:196)
+  common(d);
+  d.a = bf(wl.x[p->nb]); d.a_rows = (int)wl.rows[p->nb]; d.a_ld = C;
+  d.w = p->shrink.w; d.taps = 1; d.k_per_tap = C; d.n_pad = p->c_out_pad;
+  d.out_rows = (int)wl.rows[p->nb];
+  d.scale = t->shrink_affine; d.shift = t->shrink_affine + p->c_out_pad;
+  d.out_f32 = y; d.out_f32_ld = p->c_out_raw; d.n_valid = p->c_out_raw;
+  VP3D_TRY(run_conv(&d, stream));
+  ++launches;
+  p->last_launches = launches;
+  t->have_forward = true;
+  return VP3D_OK;
+}
+
+VP3D_API int vp3d_backward(vp3d_plan* p, const float* dy, const vp3d_grads* g, void* ws,
+                           size_t ws_bytes, void* stream_) {
+  if (!p || !dy || !g) return fail(VP3D_ERR_INVALID, "backward: null argument");
+  TrainState* t = p->train;
+  if (!t || !t->have_forward) return fail(VP3D_ERR_STATE, "backward: no training forward to match");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int N = t->N, C = p->C, pl = p->planes;
+  const int* L = t->L;
+  const int* fw = p->cfg.filter_widths;
+  const TrainLayout wl = train_layout(p, N, L);
+  if (!ws || ws_bytes < wl.total) return fail(VP3D_ERR_WORKSPACE, "backward: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
+  float* partial = reinterpret_cast<float*>(base + wl.partial);
+  if (!g->expand_conv_weight || !g->shrink_weight || !g->shrink_bias || !g->expand_bn[0] ||
+      !g->expand_bn[1])
+    return fail(VP3D_ERR_INVALID, "backward: missing gradient buffer");
+  for (int l = 0; l < 2 * p->nb; ++l)
+    if (!g->layers_conv_weight[l] || !g->layers_bn[l][0] || !g->layers_bn[l][1])
+      return fail(VP3D_ERR_INVALID, "backward: missing gradient buffer for layer %d", l);
+  int launches = 0;
+  const int co128 = c_out_pad128(p);
+  const long long rows_top = wl.rows[p->nb];
+
+  vp3d_conv_desc d;
+  auto common = [&](vp3d_conv_desc& q) {
+    memset(&q, 0, sizeof(q));
+    q.a_planes = pl;
+    q.precision = p->cfg.precision;
+    q.out_planes = pl;
+    q.samples = 1;
+    q.per_sample_tiles = 0;
+  };
+  // BN + ReLU + dropout backward of `layer`: (gin, z) -> dz (+ dgamma, dbeta)
+  auto bn_bwd = [&](int layer, long long rows, const __nv_bfloat16* gin, const __nv_bfloat16* z,
+                    float* dgamma, float* dbeta) -> int {
+    const LayerVec v = layer_vec(p, layer);
+    const DropoutCfg dc = drop_cfg(t, layer);
+    CUDA_TRY(launch_bn_bwd_reduce(gin, rows * C, z, rows * C, pl, rows, C, v.scale, v.shift, v.mean,
+                                  v.invstd, dc, v.sums, stream));
+    CUDA_TRY(launch_bn_bwd_apply(gin, rows * C, z, rows * C, bf(wl.dz), rows * C, pl, rows, C,
+                                 v.scale, v.shift, v.mean, v.invstd, dc, v.sums, dgamma, dbeta,
+                                 stream));
+    launches += 2;
+    return VP3D_OK;
+  };
+
+  // ---- shrink backward: y = X_nb * Wsh^T + b
+  CUDA_TRY(launch_pack_input(dy, bf(wl.dyp), pl, 1, (int)rows_top, p->c_out_raw, (int)rows_top, 1, 1,
+                             co128, rows_top * co128, stream));
+  CUDA_TRY(cudaMemsetAsync(g->shrink_bias, 0, p->c_out_raw * sizeof(float), stream));
+  CUDA_TRY(launch_col_sum_f32(dy, rows_top, p->c_out_raw, g->shrink_bias, stream));
+  launches += 2;
+  VP3D_TRY(run_wgrad(p, bf(wl.dyp), co128, bf(wl.x[p->nb]), C, rows_top, 1, 0, p->c_out_raw, C, C, 1,
+                     0, g->shrink_weight, partial, wl.partial_bytes, stream));
+  launches += 2;
+  __nv_bfloat16* gb[2] = {bf(wl.g0), bf(wl.g1)};
+  int cur = 0;
+  common(d);
+  d.a = bf(wl.dyp); d.a_rows = (int)rows_top; d.a_ld = co128;
+  d.w = t->shrink_t; d.taps = 1; d.k_per_tap = co128; d.n_pad = C;
+  d.out_rows = (int)rows_top;
+  d.out = gb[cur]; d.out_plane_stride = rows_top * C; d.out_ld = C;
+  VP3D_TRY(run_conv(&d, stream));
+  ++launches;
+
+  // ---- residual blocks, top-down
+  for (int i = p->nb; i >= 1; --i) {
+    const long long rows = wl.rows[i];
+    const int l1 = 2 * i - 1, l2 = 2 * i;
+    const int c1 = 2 * (i - 1), c2 = c1 + 1;
+    // second conv (1x1): X_i = res + act(bn(conv2(H_i)))
+    VP3D_TRY(bn_bwd(l2, rows, gb[cur], bf(wl.z[l2]), g->layers_bn[c2][0], g->layers_bn[c2][1]));
+    VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.h[i]), C, rows, 1, 0, C, C, C, 1, 0,
+                       g->layers_conv_weight[c2], partial, wl.partial_bytes, stream));
+    launches += 2;
+    common(d);
+    d.a = bf(wl.dz); d.a_rows = (int)rows; d.a_ld = C;
+    d.w = t->conv_t[c2]; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
+    d.out_rows = (int)rows;
+    d.out = gb[cur ^ 1]; d.out_plane_stride = rows * C; d.out_ld = C;
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+    // first conv (w taps, stride w): H_i = act(bn(conv1(X_{i-1})))
+    VP3D_TRY(bn_bwd(l1, rows, gb[cur ^ 1], bf(wl.z[l1]), g->layers_bn[c1][0], g->layers_bn[c1][1]));
+    VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.x[i - 1]), fw[i] * C, rows, p->taps[i], C, C, C, C,
+                       p->taps[i], 0, g->layers_conv_weight[c1], partial, wl.partial_bytes, stream));
+    launches += 2;
+    // G_{i-1}[rows, w*C] = dZ1 * W1^T  (+ G_i in the columns of the residual tap)
+    common(d);
+    d.a = bf(wl.dz); d.a_rows = (int)rows; d.a_ld = C;
+    d.w = t->conv_t[c1]; d.taps = 1; d.k_per_tap = C; d.n_pad = p->taps[i] * C;
+    d.out_rows = (int)rows;
+    d.out = gb[cur ^ 1]; d.out_plane_stride = rows * fw[i] * C; d.out_ld = fw[i] * C;
+    d.res = gb[cur]; d.res_planes = pl; d.res_plane_stride = rows * C; d.res_ld = C;
+    d.res_rows_per_sample = 0; d.res_row_step = 1; d.res_row_off = 0;
+    d.res_col_begin = (fw[i] / 2 + p->shift_str[i]) * C; d.res_cols = C;
+    VP3D_TRY(run_conv(&d, stream));
+    ++launches;
+    cur ^= 1;
+  }
+
+  // ---- expand backward (no data gradient: the 2-D input needs none, run.py:402-412)
+  VP3D_TRY(bn_bwd(0, wl.rows[0], gb[cur], bf(wl.z[0]), g->expand_bn[0], g->expand_bn[1]));
+  VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.a0), p->k0_pad, wl.rows[0], 1, 0, C,
+                     fw[0] * p->c_in_raw, p->c_in_raw, fw[0], 1, g->expand_conv_weight, partial,
+                     wl.partial_bytes, stream));
+  launches += 2;
+  p->last_launches = launches;
+  return VP3D_OK;
+}

@@ -1,0 +1,352 @@
+#include "train_ops.cuh"
+
+namespace vp3d {
+
+namespace {
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 8 consecutive channels of one row, summed over the hi/lo planes.
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, long long plane, int planes,
+                                      float (&v)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  v[0] = bf_lo(u.x); v[1] = bf_hi(u.x); v[2] = bf_lo(u.y); v[3] = bf_hi(u.y);
+  v[4] = bf_lo(u.z); v[5] = bf_hi(u.z); v[6] = bf_lo(u.w); v[7] = bf_hi(u.w);
+  if (planes == 2) {
+    u = __ldg(reinterpret_cast<const uint4*>(p + plane));
+    v[0] += bf_lo(u.x); v[1] += bf_hi(u.x); v[2] += bf_lo(u.y); v[3] += bf_hi(u.y);
+    v[4] += bf_lo(u.z); v[5] += bf_hi(u.z); v[6] += bf_lo(u.w); v[7] += bf_hi(u.w);
+  }
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* p, long long plane, int planes,
+                                       const float (&v)[8]) {
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = pack2(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (planes == 2) {
+    uint32_t l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      l[j] = pack2(v[2 * j] - bf_lo(h[j]), v[2 * j + 1] - bf_hi(h[j]));
+    *reinterpret_cast<uint4*>(p + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// Counter-based dropout mask: one 32-bit mix per pair of elements, 16 random bits per element.
+// keep <=> u16 >= p * 65536.  Forward and backward call this with the same (seed, layer, element).
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ void dropout_keep8(const DropoutCfg& d, long long elem0, uint32_t thresh,
+                                              float inv_keep, float (&m)[8]) {
+  const unsigned long long pair0 = (unsigned long long)elem0 >> 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned long long pr = pair0 + j;
+    uint32_t h = mix32((uint32_t)pr * 0x9E3779B1u + d.seed_lo);
+    h = mix32(h ^ ((uint32_t)(pr >> 32) * 0x7F4A7C15u + d.seed_hi + d.layer * 0x632BE5ABu));
+    m[2 * j] = ((h & 0xFFFFu) >= thresh) ? inv_keep : 0.0f;
+    m[2 * j + 1] = ((h >> 16) >= thresh) ? inv_keep : 0.0f;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, long long n,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean,
+                                   float* __restrict__ invstd, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double m = (double)stats[i] / (double)n;
+  double var = (double)stats[c + i] / (double)n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[i] * is;
+  scale[i] = sc;
+  shift[i] = beta[i] - (float)m * sc;
+  mean[i] = (float)m;
+  invstd[i] = is;
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running_mean[i] = (float)((1.0 - momentum) * running_mean[i] + momentum * m);
+    running_var[i] = (float)((1.0 - momentum) * running_var[i] + momentum * unbiased);
+  }
+}
+
+__device__ __forceinline__ long long map_row(const RowMap& m, long long r) {
+  if (m.div > 0) {
+    const long long s = r / m.div;
+    const long long t = r - s * m.div;
+    return s * m.rows_per_sample + t * m.step + m.off;
+  }
+  return r * m.step + m.off;
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
+                                __nv_bfloat16* __restrict__ x, long long x_plane, int planes,
+                                long long rows, int c, const float* __restrict__ scale,
+                                const float* __restrict__ shift, DropoutCfg drop,
+                                const __nv_bfloat16* __restrict__ res, long long res_plane,
+                                RowMap map) {
+  const int groups = c >> 3;
+  const long long total = rows * groups;
+  const bool do_drop = drop.p > 0.0f;
+  const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
+  const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long r = i / groups;
+    const int c0 = g * 8;
+    float v[8];
+    load8(z + r * c + c0, z_plane, planes, v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+    v[0] = fmaxf(fmaf(v[0], s0.x, b0.x), 0.f); v[1] = fmaxf(fmaf(v[1], s0.y, b0.y), 0.f);
+    v[2] = fmaxf(fmaf(v[2], s0.z, b0.z), 0.f); v[3] = fmaxf(fmaf(v[3], s0.w, b0.w), 0.f);
+    v[4] = fmaxf(fmaf(v[4], s1.x, b1.x), 0.f); v[5] = fmaxf(fmaf(v[5], s1.y, b1.y), 0.f);
+    v[6] = fmaxf(fmaf(v[6], s1.z, b1.z), 0.f); v[7] = fmaxf(fmaf(v[7], s1.w, b1.w), 0.f);
+    if (do_drop) {
+      float m[8];
+      dropout_keep8(drop, r * c + c0, thresh, inv_keep, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= m[j];
+    }
+    if (res) {
+      float rv[8];
+      load8(res + map_row(map, r) * c + c0, res_plane, planes, rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+    }
+    store8(x + r * c + c0, x_plane, planes, v);
+  }
+}
+
+// dY for 8 channels of one row.
+__device__ __forceinline__ void dy8(const __nv_bfloat16* g, long long g_plane,
+                                    const __nv_bfloat16* z, long long z_plane, int planes,
+                                    long long r, int c, int c0, const float* scale,
+                                    const float* shift, const DropoutCfg& drop, bool do_drop,
+                                    uint32_t thresh, float inv_keep, float (&dy)[8],
+                                    float (&zv)[8]) {
+  float gv[8];
+  load8(g + r * c + c0, g_plane, planes, gv);
+  load8(z + r * c + c0, z_plane, planes, zv);
+  float m[8];
+  if (do_drop) dropout_keep8(drop, r * c + c0, thresh, inv_keep, m);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float y = fmaf(zv[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+    float d = y > 0.0f ? gv[j] : 0.0f;
+    if (do_drop) d *= m[j];
+    dy[j] = d;
+  }
+}
+
+// block = 256 threads = 8 column groups (64 channels) x 32 row lanes; grid = (c/64, row chunks)
+constexpr int kRedRowsPerBlock = 512;
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
+                                     const __nv_bfloat16* __restrict__ z, long long z_plane,
+                                     int planes, long long rows, int c,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     DropoutCfg drop, float* __restrict__ sums) {
+  __shared__ float sm[2][8][64];
+  const int cg = threadIdx.x & 7;
+  const int rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * kRedRowsPerBlock;
+  const long long r_end = min(rows, r_begin + kRedRowsPerBlock);
+  const bool do_drop = drop.p > 0.0f;
+  const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
+  const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
+  float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = s2[j] = 0.0f;
+    mu[j] = __ldg(mean + c0 + j);
+    is[j] = __ldg(invstd + c0 + j);
+  }
+  for (long long r = r_begin + rl; r < r_end; r += 32) {
+    float dy[8], zv[8];
+    dy8(g, g_plane, z, z_plane, planes, r, c, c0, scale, shift, drop, do_drop, thresh, inv_keep, dy,
+        zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += dy[j];
+      s2[j] += dy[j] * (zv[j] - mu[j]) * is[j];
+    }
+  }
+  // the 4 row lanes sharing a warp: lanes differ in bits 3,4
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
+    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[0][warp][lane * 8 + j] = s1[j];
+      sm[1][warp][lane * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[which][w][col];
+    atomicAdd(sums + which * c + blockIdx.x * 64 + col, t);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
+                                    const __nv_bfloat16* __restrict__ z, long long z_plane,
+                                    __nv_bfloat16* __restrict__ dz, long long dz_plane, int planes,
+                                    long long rows, int c, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, DropoutCfg drop,
+                                    const float* __restrict__ sums, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int groups = c >> 3;
+  const long long total = rows * groups;
+  const bool do_drop = drop.p > 0.0f;
+  const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
+  const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
+  const float inv_n = 1.0f / (float)rows;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      if (dbeta) dbeta[i] = sums[i];
+      if (dgamma) dgamma[i] = sums[c + i];
+    }
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gq = (int)(i % groups);
+    const long long r = i / groups;
+    const int c0 = gq * 8;
+    float dy[8], zv[8], o[8];
+    dy8(g, g_plane, z, z_plane, planes, r, c, c0, scale, shift, drop, do_drop, thresh, inv_keep, dy,
+        zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (zv[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
+      // scale = gamma * invstd
+      o[j] = __ldg(scale + c0 + j) *
+             (dy[j] - __ldg(sums + c0 + j) * inv_n - xh * __ldg(sums + c + c0 + j) * inv_n);
+    }
+    store8(dz + r * c + c0, dz_plane, planes, o);
+  }
+}
+
+__global__ void col_sum_f32_kernel(const float* __restrict__ x, long long rows, int c,
+                                   float* __restrict__ out) {
+  // one warp per 32-row chunk; lanes stride the channels
+  const long long r0 = (long long)blockIdx.x * 64;
+  for (int col = threadIdx.x; col < c; col += blockDim.x) {
+    float s = 0.0f;
+    for (long long r = r0; r < min(rows, r0 + 64); ++r) s += x[r * c + col];
+    atomicAdd(out + col, s);
+  }
+}
+
+__global__ void pack_conv_weight_t_kernel(const float* __restrict__ w,
+                                          __nv_bfloat16* __restrict__ out, int planes, int c_out,
+                                          int c_in, int taps, int n_pad, int k_pad) {
+  const long long plane_elems = (long long)taps * n_pad * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane_elems;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % k_pad);
+    const int ci = (int)((i / k_pad) % n_pad);
+    const int tap = (int)(i / ((long long)k_pad * n_pad));
+    float v = 0.0f;
+    if (co < c_out && ci < c_in) v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (planes == 2) out[plane_elems + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+cudaError_t launch_bn_finalize(const float* stats, long long n, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               float* scale, float* shift, float* mean, float* invstd, int c,
+                               cudaStream_t stream) {
+  bn_finalize_kernel<<<(c + 255) / 256, 256, 0, stream>>>(stats, n, gamma, beta, running_mean,
+                                                          running_var, momentum, eps, scale, shift,
+                                                          mean, invstd, c);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bfloat16* x,
+                            long long x_plane, int planes, long long rows, int c, const float* scale,
+                            const float* shift, DropoutCfg drop, const __nv_bfloat16* res,
+                            long long res_plane, RowMap map, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  bn_apply_kernel<<<grid_for(rows * (c >> 3), 256), 256, 0, stream>>>(
+      z, z_plane, x, x_plane, planes, rows, c, scale, shift, drop, res, res_plane, map);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
+                                 long long z_plane, int planes, long long rows, int c,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, DropoutCfg drop, float* sums,
+                                 cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  dim3 grid(c / 64, (unsigned)((rows + kRedRowsPerBlock - 1) / kRedRowsPerBlock));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
+                                                 shift, mean, invstd, drop, sums);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
+                                long long z_plane, __nv_bfloat16* dz, long long dz_plane, int planes,
+                                long long rows, int c, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, DropoutCfg drop,
+                                const float* sums, float* dgamma, float* dbeta, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  bn_bwd_apply_kernel<<<grid_for(rows * (c >> 3), 256), 256, 0, stream>>>(
+      g, g_plane, z, z_plane, dz, dz_plane, planes, rows, c, scale, shift, mean, invstd, drop, sums,
+      dgamma, dbeta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out,
+                               cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  col_sum_f32_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, stream>>>(x, rows, c, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
+                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream) {
+  const long long total = (long long)taps * n_pad * k_pad;
+  pack_conv_weight_t_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, out, planes, c_out, c_in,
+                                                                      taps, n_pad, k_pad);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

@@ -1,0 +1,64 @@
+// Bandwidth-bound training-mode kernels around the GEMMs: BatchNorm1d batch statistics ->
+// affine (+ running-stat update), BN-apply + ReLU + Dropout + residual, and the BatchNorm / ReLU /
+// Dropout backward (two-pass: per-channel reductions, then dZ).  Reference semantics:
+// nn.BatchNorm1d(momentum) train mode (model.py:32,117,119), nn.ReLU, nn.Dropout(p) (model.py:28-29)
+// and the residual slice-add (model.py:130-135, 191-194).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vp3d {
+
+struct RowMap {          // residual row of output row r: (r / div)*rows_per_sample + (r % div)*step + off
+  int div;               // 0: no split (row = r*step + off)
+  int rows_per_sample;
+  int step;
+  int off;
+};
+
+struct DropoutCfg {
+  float p;               // drop probability (0 = identity)
+  uint32_t seed_lo, seed_hi;
+  uint32_t layer;        // decorrelates layers sharing a seed
+};
+
+// stats: [2][c] sum / sum of squares over n rows.  Writes scale = gamma*invstd, shift = beta -
+// mean*scale, mean, invstd and updates running_mean / running_var in place
+// (running = (1-m)*running + m*batch, unbiased variance for running_var).
+cudaError_t launch_bn_finalize(const float* stats, long long n, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               float* scale, float* shift, float* mean, float* invstd, int c,
+                               cudaStream_t stream);
+
+// x = dropout(relu(z*scale + shift)) [+ res[map(row)]]; z, x, res: bf16 [planes][rows][c].
+cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bfloat16* x,
+                            long long x_plane, int planes, long long rows, int c, const float* scale,
+                            const float* shift, DropoutCfg drop, const __nv_bfloat16* res,
+                            long long res_plane, RowMap map, cudaStream_t stream);
+
+// sums[0][c] = sum_rows dY, sums[1][c] = sum_rows dY * xhat, with
+// dY = g * dropmask/(1-p) * [z*scale+shift > 0], xhat = (z - mean) * invstd.  sums must be zeroed.
+cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
+                                 long long z_plane, int planes, long long rows, int c,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, DropoutCfg drop, float* sums,
+                                 cudaStream_t stream);
+
+// dz = scale * (dY - sums[0]/n - xhat * sums[1]/n); also writes dgamma = sums[1], dbeta = sums[0]
+// (done by block 0).  dz: bf16 [planes][rows][c].
+cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
+                                long long z_plane, __nv_bfloat16* dz, long long dz_plane, int planes,
+                                long long rows, int c, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, DropoutCfg drop,
+                                const float* sums, float* dgamma, float* dbeta, cudaStream_t stream);
+
+// out[c] = sum_rows x[row][c] for fp32 x [rows][c] (shrink.bias gradient).  out must be zeroed.
+cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out, cudaStream_t stream);
+
+// Transposed weight pack for dgrad: w fp32 (c_out, c_in, taps) -> bf16 [planes][taps][n_pad][k_pad]
+// with out[pl][tap][ci][co] = w[co][ci][tap]  (rows = input channels, K = output channels).
+cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
+                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream);
+
+}  // namespace vp3d

@@ -16,11 +16,12 @@ import torch.nn as nn
 
 from . import _capi
 
-_PRECISIONS = {"bf16": _capi.VP3D_PRECISION_BF16, "bf16x3": _capi.VP3D_PRECISION_BF16X3}
+_PRECISIONS = {"bf16": _capi.VP3D_PRECISION_BF16, "bf16x3": _capi.VP3D_PRECISION_BF16X3,
+               "mixed": _capi.VP3D_PRECISION_MIXED}
 
 
 def _default_precision():
-    p = os.environ.get("VP3D_PRECISION", "bf16")
+    p = os.environ.get("VP3D_PRECISION", "mixed")
     if p not in _PRECISIONS:
         raise ValueError(f"VP3D_PRECISION must be one of {sorted(_PRECISIONS)}, got {p!r}")
     return p
@@ -58,9 +59,13 @@ class TemporalModelBase(nn.Module):
         self._causal = bool(causal)
         self._dense = False
         self._precision = _default_precision()
+        self._train_precision = os.environ.get("VP3D_TRAIN_PRECISION", "bf16")
         self._plan = None
         self._plan_key = None
-        self._packed_versions = None
+        self._plans = {}
+        self._packed = {}
+        self._stats_epoch = 0      # bumped by every training forward (running stats changed)
+        self._fwd_token = 0        # identifies the most recent training forward
         self._workspace = None
 
     def _build_layers(self, strided):
@@ -131,12 +136,12 @@ class TemporalModelBase(nn.Module):
 
     # ------------------------------------------------------------------ engine controls
     def set_precision(self, precision):
-        """'bf16' (fast path) or 'bf16x3' (split-bf16, fp32-faithful).  Not in the reference."""
+        """'mixed' (default: bf16 on the FLOP-dominant blocks, split-bf16 on the cheap layers,
+        exact residual stream), 'bf16' (every GEMM plain bf16) or 'bf16x3' (every GEMM split-bf16,
+        fp32-faithful).  Not in the reference."""
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
-        if precision != self._precision:
-            self._precision = precision
-            self._release_plan()
+        self._precision = precision
         return self
 
     @property
@@ -144,14 +149,16 @@ class TemporalModelBase(nn.Module):
         return self._precision
 
     def _release_plan(self):
-        if self._plan is not None:
-            try:
-                _capi.load().vp3d_plan_destroy(self._plan)
-            except Exception:  # pragma: no cover - interpreter shutdown
-                pass
+        plans = getattr(self, "_plans", None)
+        if plans:
+            for handle in plans.values():
+                try:
+                    _capi.load().vp3d_plan_destroy(handle)
+                except Exception:  # pragma: no cover - interpreter shutdown
+                    pass
+        self._plans = {}
+        self._packed = {}
         self._plan = None
-        self._plan_key = None
-        self._packed_versions = None
 
     def __del__(self):
         try:
@@ -159,7 +166,7 @@ class TemporalModelBase(nn.Module):
         except Exception:  # pragma: no cover
             pass
 
-    def _config(self):
+    def _config(self, precision):
         cfg = _capi.Config()
         cfg.num_joints_in = self.num_joints_in
         cfg.in_features = self.in_features
@@ -173,23 +180,24 @@ class TemporalModelBase(nn.Module):
         cfg.channels = self._channels
         cfg.dense = int(self._dense)
         cfg.variant = self._variant
-        cfg.precision = _PRECISIONS[self._precision]
+        cfg.precision = _PRECISIONS[precision]
         return cfg
 
-    def _get_plan(self, device):
-        key = (device.index, self._precision)
-        if self._plan is None or self._plan_key != key:
-            self._release_plan()
+    def _get_plan(self, device, precision=None):
+        precision = precision or self._precision
+        key = (device.index, precision)
+        plans = self.__dict__.setdefault("_plans", {})
+        if key not in plans:
             lib = _capi.load()
             handle = _capi.ctypes.c_void_p()
-            cfg = self._config()
+            cfg = self._config(precision)
             with torch.cuda.device(device):
                 _capi.check(lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(handle)),
                             "vp3d_plan_create")
-            self._plan = handle
-            self._plan_key = key
-            self._packed_versions = None
-        return self._plan
+            plans[key] = handle
+        self._plan = plans[key]
+        self._plan_key = key
+        return plans[key]
 
     def _param_tensors(self):
         """All fp32 tensors of the state_dict in the order of ``vp3d_weights``."""
@@ -201,20 +209,7 @@ class TemporalModelBase(nn.Module):
         bn.append(self.shrink.bias)
         return conv, bn
 
-    def _sync_weights(self, plan, stream):
-        conv, bn = self._param_tensors()
-        versions = (tuple((t.data_ptr(), t._version) for t in conv),
-                    tuple((t.data_ptr(), t._version) for t in bn))
-        what = 0
-        if self._packed_versions is None or self._packed_versions[0] != versions[0]:
-            what |= _capi.VP3D_PACK_CONV
-        if self._packed_versions is None or self._packed_versions[1] != versions[1]:
-            what |= _capi.VP3D_PACK_BN_EVAL
-        if not what:
-            return
-        for t in conv + bn:
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise RuntimeError("parameters must be contiguous float32 tensors")
+    def _weights_struct(self):
         w = _capi.Weights()
         w.expand_conv_weight = self.expand_conv.weight.data_ptr()
         for k, t in enumerate((self.expand_bn.weight, self.expand_bn.bias,
@@ -227,9 +222,34 @@ class TemporalModelBase(nn.Module):
                 w.layers_bn[i][k] = t.data_ptr()
         w.shrink_weight = self.shrink.weight.data_ptr()
         w.shrink_bias = self.shrink.bias.data_ptr()
+        return w
+
+    def _sync_weights(self, plan, stream, training=False):
+        """Re-pack whatever changed since this plan last saw the parameters (optimizer.step,
+        load_state_dict, in-place edits; the training kernels' running-stat updates are tracked
+        through ``_stats_epoch`` because they bypass torch's version counters)."""
+        conv, bn = self._param_tensors()
+        versions = (tuple((t.data_ptr(), t._version) for t in conv),
+                    tuple((t.data_ptr(), t._version) for t in bn) + (self._stats_epoch,))
+        packed = self.__dict__.setdefault("_packed", {})
+        key = (self._plan_key, training)
+        seen = packed.get(key)
+        what = 0
+        if seen is None or seen[0] != versions[0]:
+            what |= _capi.VP3D_PACK_CONV
+            if training:
+                what |= _capi.VP3D_PACK_CONV_T
+        if not training and (seen is None or seen[1] != versions[1]):
+            what |= _capi.VP3D_PACK_BN_EVAL
+        if not what:
+            return
+        for t in conv + bn:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("parameters must be contiguous float32 tensors")
+        w = self._weights_struct()
         _capi.check(_capi.load().vp3d_set_weights(plan, _capi.ctypes.byref(w), what, stream),
                     "vp3d_set_weights")
-        self._packed_versions = versions
+        packed[key] = versions
 
     def _get_workspace(self, nbytes, device):
         ws = self._workspace
@@ -277,8 +297,28 @@ class TemporalModelBase(nn.Module):
         return y
 
     def _forward_train(self, x):
-        raise NotImplementedError("training-mode forward/backward kernels are not built yet "
-                                  "(round-1 scope: eval forward); call .eval() first")
+        if self._variant != _capi.VP3D_VARIANT_STRIDED:
+            raise NotImplementedError(
+                "training kernels cover TemporalModelOptimized1f (the model run.py trains with); "
+                "TemporalModel in train() mode is not built yet — there is no PyTorch fallback")
+        params = self._learnable_tensors()
+        return _TrainFunction.apply(self, x.contiguous(), *params)
+
+    def _learnable_tensors(self):
+        """Learnable tensors in the order of ``vp3d_grads``."""
+        out = [self.expand_conv.weight, self.expand_bn.weight, self.expand_bn.bias]
+        out += [c.weight for c in self.layers_conv]
+        for m in self.layers_bn:
+            out += [m.weight, m.bias]
+        out += [self.shrink.weight, self.shrink.bias]
+        return out
+
+    def set_train_precision(self, precision):
+        """'bf16' (default) or 'bf16x3' (fp32-faithful gradients) for the training kernels."""
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("train precision must be 'bf16' or 'bf16x3'")
+        self._train_precision = precision
+        return self
 
     def forward_host(self, x_host, out=None):
         """Eval forward from a HOST float32 tensor/array (pinned for full PCIe speed): copies the
@@ -313,6 +353,83 @@ class TemporalModelBase(nn.Module):
 
     def last_launch_count(self):
         return 0 if self._plan is None else _capi.load().vp3d_last_launch_count(self._plan)
+
+
+class _TrainFunction(torch.autograd.Function):
+    """Training-mode forward/backward through the C ABI (vp3d_forward_train / vp3d_backward).
+
+    The learnable tensors are passed as inputs so that autograd accumulates the returned
+    gradients into ``.grad`` exactly as it does for the reference's nn modules."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        lib = _capi.load()
+        device = x.device
+        N, T = int(x.shape[0]), int(x.shape[1])
+        momenta = [module.expand_bn.momentum] + [bn.momentum for bn in module.layers_bn]
+        if any(m is None for m in momenta):
+            raise NotImplementedError("BatchNorm momentum=None (cumulative average) is not supported")
+        p_drop = float(module.drop.p)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: torch.manual_seed applies
+        with torch.cuda.device(device):
+            plan = module._get_plan(device, module._train_precision)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            module._sync_weights(plan, stream, training=True)
+            t_out = lib.vp3d_output_frames(plan, T)
+            nbytes = lib.vp3d_train_workspace_bytes(plan, N, T)
+            if t_out < 1 or nbytes == 0:
+                raise ValueError(f"input of {T} frames is shorter than the receptive field "
+                                 f"({module.receptive_field()})")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            y = torch.empty((N, t_out, module.num_joints_out, 3), dtype=torch.float32, device=device)
+            w = module._weights_struct()
+            mom = (_capi.ctypes.c_float * len(momenta))(*[float(m) for m in momenta])
+            _capi.check(lib.vp3d_forward_train(plan, x.data_ptr(), y.data_ptr(), N, T,
+                                               _capi.ctypes.byref(w), mom, p_drop, seed,
+                                               ws.data_ptr(), ws.numel(), stream),
+                        "vp3d_forward_train")
+        # nn.BatchNorm1d bookkeeping that lives outside the kernels
+        with torch.no_grad():
+            module.expand_bn.num_batches_tracked += 1
+            for bn in module.layers_bn:
+                bn.num_batches_tracked += 1
+        module._stats_epoch += 1
+        module._fwd_token += 1
+        ctx.module = module
+        ctx.plan = plan
+        ctx.ws = ws
+        ctx.token = module._fwd_token
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.device = device
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        module = ctx.module
+        if ctx.token != module._fwd_token:
+            raise RuntimeError("only the most recent training forward of a module can be "
+                               "back-propagated (one forward per backward, as in run.py)")
+        lib = _capi.load()
+        device = ctx.device
+        dy = dy.contiguous().float()
+        grads = [torch.empty(s, dtype=torch.float32, device=device) for s in ctx.shapes]
+        nb2 = len(module.layers_conv)
+        g = _capi.Grads()
+        g.expand_conv_weight = grads[0].data_ptr()
+        g.expand_bn[0] = grads[1].data_ptr()
+        g.expand_bn[1] = grads[2].data_ptr()
+        for i in range(nb2):
+            g.layers_conv_weight[i] = grads[3 + i].data_ptr()
+            g.layers_bn[i][0] = grads[3 + nb2 + 2 * i].data_ptr()
+            g.layers_bn[i][1] = grads[3 + nb2 + 2 * i + 1].data_ptr()
+        g.shrink_weight = grads[3 + 3 * nb2].data_ptr()
+        g.shrink_bias = grads[3 + 3 * nb2 + 1].data_ptr()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _capi.check(lib.vp3d_backward(ctx.plan, dy.data_ptr(), _capi.ctypes.byref(g),
+                                          ctx.ws.data_ptr(), ctx.ws.numel(), stream), "vp3d_backward")
+        ctx.ws = None
+        return (None, None) + tuple(grads)
 
 
 class TemporalModel(TemporalModelBase):
