@@ -68,12 +68,24 @@ CASES = {
 
 
 def build_case(name, cfg):
-    seed = abs(hash(name)) % 1000 if False else sum(ord(c) for c in name)  # stable across runs
+    seed = sum(ord(c) for c in name)  # stable across runs
     causal = bool(cfg.get("causal", False))
     dense = bool(cfg.get("dense", False))
-    sd = orc.make_state_dict(cfg["J"], cfg["F"], cfg["Jout"], cfg["fw"], cfg["C"], dense=dense,
-                             seed=seed)
-    x = orc.make_input(cfg["N"], cfg["T"], cfg["J"], cfg["F"], seed=seed + 1)
+    while True:
+        sd = orc.make_state_dict(cfg["J"], cfg["F"], cfg["Jout"], cfg["fw"], cfg["C"], dense=dense,
+                                 seed=seed)
+        x = orc.make_input(cfg["N"], cfg["T"], cfg["J"], cfg["F"], seed=seed + 1)
+        if not (cfg.get("train") and cfg["cls"] == "TemporalModelOptimized1f"):
+            break
+        # Gradient parity at 1e-3 is only well-posed away from ReLU kinks: a pre-activation within
+        # rounding error of zero flips its mask and moves gradients by O(1/rows).  Keep seeds whose
+        # smallest |pre-activation| is >= 2e-4 (checked with the float64 emulation).
+        from oracle import train_emulation as emu
+        probe = emu.train_step(sd, x, torch.zeros(cfg["N"], 1, cfg["Jout"], 3), cfg["fw"],
+                               causal=causal, planes=0, momentum=cfg["momentum"])
+        if probe["min_abs_preact"] >= 2e-4:
+            break
+        seed += 1000
     kw = dict(filter_widths=cfg["fw"], causal=causal, dropout=0.0, channels=cfg["C"])
     if cfg["cls"] == "TemporalModel":
         model = TemporalModel(cfg["J"], cfg["F"], cfg["Jout"], dense=dense, **kw)

@@ -86,3 +86,24 @@ def test_arch_bookkeeping():
     assert orc.arch([3, 3, 3], causal=True, strided=True)["shift"] == [1, 1, 1]
     with pytest.raises(AssertionError):
         orc.arch([3, 4])
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("opt") and "train" in n])
+def test_train_emulation_matches_reference(name):
+    """oracle/train_emulation.py (analytic backward, float64, no rounding) == the reference's
+    autograd gradients, updated running statistics and output."""
+    from oracle import train_emulation as emu
+    meta, sd, x, y_ref, new = load_golden(name)
+    out = emu.train_step(sd, x, torch.from_numpy(new["gy"]), meta["fw"], causal=meta["causal"],
+                         planes=0, momentum=meta["momentum"])
+    assert out["min_abs_preact"] >= 2e-4, "fixture sits on a ReLU kink"
+    assert _rel(out["y"].numpy(), y_ref) < 2e-5
+    for k, v in out["grads"].items():
+        assert _rel(v.numpy(), new["grad/" + k]) < 1e-4, k
+    for k, v in out["new_stats"].items():
+        assert _rel(v.numpy(), new[k]) < 2e-5, k
+    # split-bf16 rounding points keep the step fp32-faithful on a well-conditioned fixture
+    out2 = emu.train_step(sd, x, torch.from_numpy(new["gy"]), meta["fw"], causal=meta["causal"],
+                          planes=2, momentum=meta["momentum"])
+    for k, v in out2["grads"].items():
+        assert _rel(v.numpy(), new["grad/" + k]) < 1e-3, k

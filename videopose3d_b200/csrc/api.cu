@@ -187,7 +187,16 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   if (!d->out && !d->out_f32) return fail(VP3D_ERR_INVALID, "conv_gemm: no output");
   if (d->out && (d->out_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: out_ld % 8 != 0");
   if (d->res && (d->res_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: res_ld % 8 != 0");
-  CUDA_TRY(launch_conv_gemm(ma, mw, g, block_n, num_sms(), stream));
+  CUtensorMap mo = ma;
+  if (d->out) {
+    const uint64_t o_rows = d->out_rows, o_ld = d->out_ld;
+    const uint64_t o_samples = d->per_sample_tiles ? d->samples : 1;
+    uint64_t o_plane = (uint64_t)d->out_plane_stride;
+    if (g.out_planes == 1 || o_plane == 0) o_plane = o_samples * o_rows * o_ld;
+    VP3D_TRY(make_map_4d(&mo, d->out, o_ld, o_rows, o_ld, o_samples, o_rows * o_ld, g.out_planes,
+                         o_plane, kBlockM));
+  }
+  CUDA_TRY(launch_conv_gemm(ma, mw, mo, g, block_n, num_sms(), stream));
   return VP3D_OK;
 }
 

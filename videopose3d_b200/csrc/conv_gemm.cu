@@ -4,7 +4,9 @@
 //   warp 0 lane 0 : TMA producer  (A tile 128x64 bf16 + W tile BLOCK_Nx64 bf16 per k-block)
 //   warp 1 lane 0 : tcgen05.mma issuer (4 x K=16 MMAs per k-block, accumulator in TMEM)
 //   warp 2        : TMEM allocator / deallocator
-//   warps 4..7    : epilogue (tcgen05.ld -> BN affine / ReLU / residual / stats -> global)
+//   warps 4..7    : epilogue: tcgen05.ld -> BN affine / ReLU / residual / batch sums in registers
+//                   -> bf16 pack into a SWIZZLE_128B staging tile in shared memory -> TMA store
+//                   (coalesced 128-byte rows, clipped at the tensor edge by the tensor map)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
@@ -18,8 +20,10 @@ struct GemmCfg {
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr uint32_t kStoreBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 staging tile
   static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
+  // pipeline stages + 2 staging tiles + barriers + 1 KiB alignment slack
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 2 * kStoreBytes + kBarBytes + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
@@ -35,10 +39,22 @@ __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int
   }
 }
 
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                 const __grid_constant__ CUtensorMap tmap_w, const ConvGemmArgs p) {
+                 const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_out, const ConvGemmArgs p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
 
@@ -49,7 +65,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + kStages * Cfg::kABytes;
-  const uint32_t bar_base = base + kStages * Cfg::kStageBytes;
+  const uint32_t smem_store = base + kStages * Cfg::kStageBytes;  // 2 x 16 KiB, 1024-aligned
+  const uint32_t bar_base = smem_store + 2 * Cfg::kStoreBytes;
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + kStages * 8;
   const uint32_t tfull_bar = bar_base + 2 * kStages * 8;
@@ -68,6 +85,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -146,12 +164,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ------------------------------------------------------------ epilogue
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     const int r_in_tile = ew * 32 + lane;
+    const bool store_leader = (threadIdx.x == 128);
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t store_seq = 0;
     const bool do_relu = p.flags & kEpiRelu;
     const bool do_res = p.flags & kEpiResidual;
     const bool do_stats = p.flags & kEpiStats;
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
+    const bool two_planes = p.out_planes == 2;
+    // swizzled staging address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
+    const uint32_t stage_row = r_in_tile * 128;
+    const uint32_t sw = r_in_tile & 7;
+
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int n_blk, sample, row0;
       tile_coords(p, tile, n_blk, sample, row0);
@@ -177,6 +202,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        const int half = chunk & 1;  // which 32-column half of the 64-column store block
+        // staging tile for this store block: single plane -> double buffered; two planes -> tile 0
+        // holds hi, tile 1 holds lo and the previous store must have been read out first.
+        const uint32_t buf = two_planes ? 0u : (store_seq & 1u);
+        if (!do_f32 && half == 0) {
+          if (store_leader) {
+            if (two_planes) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          epi_bar_sync();
+        }
+
         uint32_t raw[32];
         tmem_ld_32x32(t_addr + chunk * 32, raw);
         tmem_ld_wait();
@@ -228,16 +264,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 32; ++j)
               if (c0 + j < p.n_valid) op[j] = v[j];
           }
-        } else if (valid) {
-          __nv_bfloat16* op = p.out + out_row * p.out_ld + c0;
+        } else {
           uint32_t hi[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          uint4* o4 = reinterpret_cast<uint4*>(op);
+          const uint32_t dst = smem_store + buf * Cfg::kStoreBytes + stage_row;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            o4[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (p.out_planes == 2) {
+            st_shared_v4(dst + (((half * 4 + q) ^ sw) << 4), hi[4 * q], hi[4 * q + 1],
+                         hi[4 * q + 2], hi[4 * q + 3]);
+          if (two_planes) {
             uint32_t lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -245,10 +281,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const float r1 = v[2 * j + 1] - bf16_hi_to_f(hi[j]);
               lo[j] = pack_bf16x2(r0, r1);
             }
-            uint4* l4 = reinterpret_cast<uint4*>(op + p.out_plane_stride);
+            const uint32_t dst_lo = smem_store + Cfg::kStoreBytes + stage_row;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              l4[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+              st_shared_v4(dst_lo + (((half * 4 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1],
+                           lo[4 * q + 2], lo[4 * q + 3]);
+          }
+          if (half == 1) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+            epi_bar_sync();
+            if (store_leader) {
+              const int col = n_blk * BLOCK_N + (chunk - 1) * 32;
+              tma_store_4d(&tmap_out, smem_store + buf * Cfg::kStoreBytes, col, row0, sample, 0);
+              if (two_planes)
+                tma_store_4d(&tmap_out, smem_store + Cfg::kStoreBytes, col, row0, sample, 1);
+              tma_store_commit();
+            }
+            ++store_seq;
           }
         }
         if (do_stats) {
@@ -282,6 +331,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_arrive(tempty_bar + acc * 8);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    // the staging tiles must outlive every bulk store that reads them
+    if (store_leader) tma_store_wait_all<0>();
   }
 
   __syncwarp();
@@ -295,7 +346,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
 template <int BLOCK_N>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                               const ConvGemmArgs& args, int num_sms, cudaStream_t stream) {
+                               const CUtensorMap& tmap_out, const ConvGemmArgs& args, int num_sms,
+                               cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -309,17 +361,17 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   const int total = m_tiles * args.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, args);
+  conv_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, args);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                             const ConvGemmArgs& args, int block_n, int num_sms,
-                             cudaStream_t stream) {
+                             const CUtensorMap& tmap_out, const ConvGemmArgs& args, int block_n,
+                             int num_sms, cudaStream_t stream) {
   switch (block_n) {
-    case 256: return launch_impl<256>(tmap_a, tmap_w, args, num_sms, stream);
-    case 128: return launch_impl<128>(tmap_a, tmap_w, args, num_sms, stream);
-    case 64: return launch_impl<64>(tmap_a, tmap_w, args, num_sms, stream);
+    case 256: return launch_impl<256>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
+    case 128: return launch_impl<128>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
+    case 64: return launch_impl<64>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

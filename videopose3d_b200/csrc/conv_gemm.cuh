@@ -74,9 +74,11 @@ struct ConvGemmArgs {
   float* stats;                // [2][n_pad] running sum / sumsq accumulators (atomicAdd)
 };
 
-// Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row).
+// Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);
+// tmap_out: 4-D (channel, row, sample, plane) over the bf16 output, box (64, 128, 1, 1) (ignored —
+// pass any valid map — when the launch writes fp32).
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                             const ConvGemmArgs& args, int block_n, int num_sms,
-                             cudaStream_t stream);
+                             const CUtensorMap& tmap_out, const ConvGemmArgs& args, int block_n,
+                             int num_sms, cudaStream_t stream);
 
 }  // namespace vp3d
