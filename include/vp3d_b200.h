@@ -149,6 +149,16 @@ int vp3d_forward_train(vp3d_plan* plan, const float* x, float* y, int N, int T, 
 int vp3d_backward(vp3d_plan* plan, const float* dy, const vp3d_grads* grads, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Same as vp3d_backward, calling stage_done(stage, user) on the host right after the kernels that
+ * produce one group of gradients have been enqueued on `stream`: stage 0 = shrink.{weight,bias};
+ * stage s = 1..B = residual block B - s + 1 (its two convs and two BatchNorms); stage B + 1 =
+ * expand_conv / expand_bn.  A data-parallel host uses it to start the all-reduce of a finished
+ * group on a side stream while the rest of the backward is still running (run.py has no
+ * counterpart: the reference is single-GPU). */
+typedef void (*vp3d_stage_fn)(int stage, void* user);
+int vp3d_backward_staged(vp3d_plan* plan, const float* dy, const vp3d_grads* grads, void* workspace,
+                         size_t workspace_bytes, void* stream, vp3d_stage_fn stage_done, void* user);
+
 /* Number of kernels the last forward on this plan launched (for bench.py's gpu_launches). */
 int vp3d_last_launch_count(const vp3d_plan* plan);
 

@@ -46,11 +46,14 @@ def train_step(sd, x, gy, filter_widths, causal=False, planes=0, momentum=0.1):
     saved, new_stats = {}, {}
     min_pre = float("inf")
 
-    def bn(z, prefix, layer):
+    def bn(z_exact, prefix, layer):
+        # the kernels take the batch statistics from the fp32 accumulators (before rounding) and
+        # normalise the stored (rounded) Z with them
         nonlocal min_pre
-        n = z.shape[0]
-        mu = z.mean(0)
-        var = z.var(0, unbiased=False)
+        n = z_exact.shape[0]
+        mu = z_exact.mean(0)
+        var = z_exact.var(0, unbiased=False)
+        z = q(z_exact)
         inv = 1.0 / torch.sqrt(var + EPS)
         sc = sd[prefix + ".weight"] * inv
         sh = sd[prefix + ".bias"] - mu * sc
@@ -66,7 +69,7 @@ def train_step(sd, x, gy, filter_widths, causal=False, planes=0, momentum=0.1):
     L0 = T // fw[0]
     a0 = q(x.reshape(N, T, c_in)[:, :L0 * fw[0]].reshape(N * L0, fw[0] * c_in))
     w0 = sd["expand_conv.weight"].permute(0, 2, 1).reshape(C, -1)       # [co][tap*c_in + ci]
-    X = q(bn(q(a0 @ q(w0).T), "expand_bn", 0))
+    X = q(bn(a0 @ q(w0).T, "expand_bn", 0))
     Xs, Hs = [X], [None]
     nb = len(fw) - 1
     offs = [None]
@@ -75,9 +78,9 @@ def train_step(sd, x, gy, filter_widths, causal=False, planes=0, momentum=0.1):
         rows = X.shape[0] // w
         A = X.reshape(rows, w * C)
         w1 = sd[f"layers_conv.{2 * (i - 1)}.weight"].permute(0, 2, 1).reshape(C, w * C)
-        H = q(bn(q(A @ q(w1).T), f"layers_bn.{2 * (i - 1)}", 2 * i - 1))
+        H = q(bn(A @ q(w1).T, f"layers_bn.{2 * (i - 1)}", 2 * i - 1))
         w2 = sd[f"layers_conv.{2 * (i - 1) + 1}.weight"][:, :, 0]
-        Y2 = bn(q(H @ q(w2).T), f"layers_bn.{2 * (i - 1) + 1}", 2 * i)
+        Y2 = bn(H @ q(w2).T, f"layers_bn.{2 * (i - 1) + 1}", 2 * i)
         off = w // 2 + (w // 2 if causal else 0)                           # model.py:191
         X = q(X.reshape(rows, w, C)[:, off] + Y2)
         Xs.append(X)
@@ -120,6 +123,12 @@ def train_step(sd, x, gy, filter_widths, causal=False, planes=0, momentum=0.1):
     grads["expand_conv.weight"] = (dz0.T @ a0).reshape(C, fw[0], c_in).permute(0, 2, 1)
     return dict(y=y.reshape(N, -1, y.shape[1] // 3, 3), grads=grads, new_stats=new_stats,
                 min_abs_preact=min_pre)
+
+
+def rel_l2(a, b):
+    a = a.detach().cpu().double().numpy() if hasattr(a, "detach") else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if hasattr(b, "detach") else np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
 def rel_max(a, b):

@@ -24,6 +24,7 @@ _LIB_NAME = "libvp3d_b200.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", _LIB_NAME)
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
+STAGE_FN = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
 
 
 class Config(ctypes.Structure):
@@ -129,6 +130,9 @@ SIGNATURES = {
                                           ctypes.c_void_p]),
     "vp3d_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Grads),
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "vp3d_backward_staged": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Grads),
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "vp3d_last_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "vp3d_profile_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "vp3d_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),

@@ -327,8 +327,22 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   return VP3D_OK;
 }
 
+static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, void* ws,
+                         size_t ws_bytes, void* stream_, vp3d_stage_fn stage_done, void* user);
+
 VP3D_API int vp3d_backward(vp3d_plan* p, const float* dy, const vp3d_grads* g, void* ws,
                            size_t ws_bytes, void* stream_) {
+  return backward_impl(p, dy, g, ws, ws_bytes, stream_, nullptr, nullptr);
+}
+
+VP3D_API int vp3d_backward_staged(vp3d_plan* p, const float* dy, const vp3d_grads* g, void* ws,
+                                  size_t ws_bytes, void* stream_, vp3d_stage_fn stage_done,
+                                  void* user) {
+  return backward_impl(p, dy, g, ws, ws_bytes, stream_, stage_done, user);
+}
+
+static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, void* ws,
+                         size_t ws_bytes, void* stream_, vp3d_stage_fn stage_done, void* user) {
   if (!p || !dy || !g) return fail(VP3D_ERR_INVALID, "backward: null argument");
   TrainState* t = p->train;
   if (!t || !t->have_forward) return fail(VP3D_ERR_STATE, "backward: no training forward to match");
@@ -392,6 +406,7 @@ VP3D_API int vp3d_backward(vp3d_plan* p, const float* dy, const vp3d_grads* g, v
   d.out = gb[cur]; d.out_plane_stride = rows_top * C; d.out_ld = C;
   VP3D_TRY(run_conv(&d, stream));
   ++launches;
+  if (stage_done) stage_done(0, user);  // shrink.weight / shrink.bias gradients are enqueued
 
   // ---- residual blocks, top-down
   for (int i = p->nb; i >= 1; --i) {
@@ -427,6 +442,7 @@ VP3D_API int vp3d_backward(vp3d_plan* p, const float* dy, const vp3d_grads* g, v
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     cur ^= 1;
+    if (stage_done) stage_done(p->nb - i + 1, user);  // all four parameter groups of block i
   }
 
   // ---- expand backward (no data gradient: the 2-D input needs none, run.py:402-412)
@@ -435,6 +451,7 @@ VP3D_API int vp3d_backward(vp3d_plan* p, const float* dy, const vp3d_grads* g, v
                      fw[0] * p->c_in_raw, p->c_in_raw, fw[0], 1, g->expand_conv_weight, partial,
                      wl.partial_bytes, stream));
   launches += 2;
+  if (stage_done) stage_done(p->nb + 1, user);  // expand_conv / expand_bn
   p->last_launches = launches;
   return VP3D_OK;
 }

@@ -1,0 +1,117 @@
+"""Data-parallel training of the temporal models: one process per GPU, batches sharded by rank,
+one gradient all-reduce per step over NCCL (NVLink 5 / NVSwitch) — SURVEY.md §8e.
+
+The reference is single-GPU (no torch.distributed anywhere), so this module has no reference
+counterpart; it adds exactly one collective.  BatchNorm statistics stay per-GPU (north_star:
+"allreduce on gradients only"); `broadcast_buffers` aligns the running statistics before a
+checkpoint / evaluation, as DistributedDataParallel does.
+
+Overlap: the C backward (`vp3d_backward_staged`) reports, stage by stage, when the kernels producing
+a group of gradients have been enqueued (shrink first, expand last).  All gradients of a step live
+in one flat fp32 buffer laid out in that completion order, so each stage is a contiguous slice whose
+all-reduce is launched on a side stream behind an event while the remaining backward GEMMs run.
+"""
+import torch
+import torch.distributed as dist
+
+
+def stage_order(module):
+    """Parameter names grouped by backward completion stage (see vp3d_backward_staged)."""
+    nb = len(module.layers_conv) // 2
+    stages = [["shrink.weight", "shrink.bias"]]
+    for i in range(nb, 0, -1):
+        c1, c2 = 2 * (i - 1), 2 * (i - 1) + 1
+        stages.append([f"layers_conv.{c2}.weight", f"layers_bn.{c2}.weight", f"layers_bn.{c2}.bias",
+                       f"layers_conv.{c1}.weight", f"layers_bn.{c1}.weight", f"layers_bn.{c1}.bias"])
+    stages.append(["expand_conv.weight", "expand_bn.weight", "expand_bn.bias"])
+    return stages
+
+
+class GradientReducer:
+    """Averages gradients across the ranks of `process_group`.
+
+    attach(module) makes the module's training backward write its gradients into a flat buffer and
+    all-reduce it stage by stage (overlapped on CUDA); `reduce_flat` is the device-agnostic core and
+    is what the CPU (gloo) tests exercise."""
+
+    def __init__(self, process_group=None, overlap=True):
+        self.group = process_group
+        self.overlap = overlap
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.comm_stream = None
+        self.launched = 0
+
+    # ---------------------------------------------------------------- layout
+    def plan_layout(self, module):
+        """-> (names in flat order, {name: (offset, numel)}, [(lo, hi)] per stage); offsets are
+        padded to 4 elements so that every slice stays 16-byte aligned."""
+        params = dict(module.named_parameters())
+        names, spans, stage_spans = [], {}, []
+        off = 0
+        for group in stage_order(module):
+            lo = off
+            for n in group:
+                numel = params[n].numel()
+                spans[n] = (off, numel)
+                names.append(n)
+                off += (numel + 3) // 4 * 4
+            stage_spans.append((lo, off))
+        return names, spans, stage_spans, off
+
+    def attach(self, module):
+        module._grad_reducer = self
+        return module
+
+    # ---------------------------------------------------------------- collective
+    def reduce_flat(self, flat):
+        """In-place average of a flat gradient slice over the group."""
+        if self.world == 1:
+            return flat
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo (CPU tests): no AVG
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        self.launched += 1
+        return flat
+
+    def stage_ready(self, flat, lo, hi):
+        """Called (from the C backward's stage callback) once the kernels writing flat[lo:hi] are
+        enqueued on the current stream."""
+        if hi <= lo:
+            return
+        piece = flat[lo:hi]
+        if not flat.is_cuda or not self.overlap:
+            self.reduce_flat(piece)
+            return
+        cur = torch.cuda.current_stream(flat.device)
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=flat.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.reduce_flat(piece)
+        flat.record_stream(self.comm_stream)
+
+    def finish(self, flat):
+        """Make the current stream wait for every outstanding all-reduce."""
+        if flat.is_cuda and self.comm_stream is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(self.comm_stream)
+
+
+def broadcast_buffers(module, src=0, process_group=None):
+    """Copy rank `src`'s BatchNorm running statistics to every rank (checkpoint / eval alignment)."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return
+    for b in module.buffers():
+        dist.broadcast(b, src=src, group=process_group)
+    if hasattr(module, "_stats_epoch"):
+        module._stats_epoch += 1
+
+
+def shard_batch(batch_index, rank, world):
+    """Weak scaling as SURVEY.md §8e prefers: rank r takes batches b with b % world == r, each of
+    the full per-GPU batch size (keeps the BatchNorm population per GPU equal to the reference's)."""
+    return batch_index % world == rank

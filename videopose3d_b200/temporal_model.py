@@ -66,6 +66,7 @@ class TemporalModelBase(nn.Module):
         self._packed = {}
         self._stats_epoch = 0      # bumped by every training forward (running stats changed)
         self._fwd_token = 0        # identifies the most recent training forward
+        self._grad_reducer = None  # data_parallel.GradientReducer, set by its attach()
         self._workspace = None
 
     def _build_layers(self, strided):
@@ -313,6 +314,14 @@ class TemporalModelBase(nn.Module):
         out += [self.shrink.weight, self.shrink.bias]
         return out
 
+    def _learnable_names(self):
+        out = ["expand_conv.weight", "expand_bn.weight", "expand_bn.bias"]
+        out += [f"layers_conv.{i}.weight" for i in range(len(self.layers_conv))]
+        for i in range(len(self.layers_bn)):
+            out += [f"layers_bn.{i}.weight", f"layers_bn.{i}.bias"]
+        out += ["shrink.weight", "shrink.bias"]
+        return out
+
     def set_train_precision(self, precision):
         """'bf16' (default) or 'bf16x3' (fp32-faithful gradients) for the training kernels."""
         if precision not in ("bf16", "bf16x3"):
@@ -412,7 +421,19 @@ class _TrainFunction(torch.autograd.Function):
         lib = _capi.load()
         device = ctx.device
         dy = dy.contiguous().float()
-        grads = [torch.empty(s, dtype=torch.float32, device=device) for s in ctx.shapes]
+        names = [n for n, _ in module.named_parameters()]
+        order = module._learnable_names()
+        reducer = getattr(module, "_grad_reducer", None)
+        if reducer is not None and reducer.world > 1:
+            # one flat buffer laid out in backward-completion order: each stage is a contiguous
+            # slice that is all-reduced on a side stream while later stages are still computing
+            _, spans, stage_spans, total = reducer.plan_layout(module)
+            flat = torch.empty(total, dtype=torch.float32, device=device)
+            by_name = {n: flat[spans[n][0]: spans[n][0] + spans[n][1]] for n in spans}
+            grads = [by_name[n].view(s) for n, s in zip(order, ctx.shapes)]
+        else:
+            flat, stage_spans = None, None
+            grads = [torch.empty(s, dtype=torch.float32, device=device) for s in ctx.shapes]
         nb2 = len(module.layers_conv)
         g = _capi.Grads()
         g.expand_conv_weight = grads[0].data_ptr()
@@ -426,8 +447,29 @@ class _TrainFunction(torch.autograd.Function):
         g.shrink_bias = grads[3 + 3 * nb2 + 1].data_ptr()
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            _capi.check(lib.vp3d_backward(ctx.plan, dy.data_ptr(), _capi.ctypes.byref(g),
-                                          ctx.ws.data_ptr(), ctx.ws.numel(), stream), "vp3d_backward")
+            if flat is None:
+                _capi.check(lib.vp3d_backward(ctx.plan, dy.data_ptr(), _capi.ctypes.byref(g),
+                                              ctx.ws.data_ptr(), ctx.ws.numel(), stream),
+                            "vp3d_backward")
+            else:
+                errors = []
+
+                def _stage(stage, _user):
+                    try:
+                        lo, hi = stage_spans[stage]
+                        reducer.stage_ready(flat, lo, hi)
+                    except Exception as e:  # never raise through the C frame
+                        errors.append(e)
+
+                cb = _capi.STAGE_FN(_stage)
+                _capi.check(lib.vp3d_backward_staged(ctx.plan, dy.data_ptr(), _capi.ctypes.byref(g),
+                                                     ctx.ws.data_ptr(), ctx.ws.numel(), stream,
+                                                     _capi.ctypes.cast(cb, _capi.ctypes.c_void_p),
+                                                     None), "vp3d_backward_staged")
+                if errors:
+                    raise errors[0]
+                reducer.finish(flat)
+        del names
         ctx.ws = None
         return (None, None) + tuple(grads)
 
