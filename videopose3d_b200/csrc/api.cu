@@ -132,7 +132,8 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     bool found = false;
     for (int c : cands) {
       if (d->n_pad % c) continue;
-      if (m_tiles * (d->n_pad / c) >= num_sms()) { block_n = c; found = true; break; }
+      // half a wave of full-rate 128x256 tiles beats a full wave of narrower (smem-bound) ones
+      if (m_tiles * (d->n_pad / c) * 2 >= num_sms()) { block_n = c; found = true; break; }
     }
     if (!found) block_n = 64;
   }
@@ -196,7 +197,44 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     VP3D_TRY(make_map_4d(&mo, d->out, o_ld, o_rows, o_ld, o_samples, o_rows * o_ld, g.out_planes,
                          o_plane, kBlockM));
   }
-  CUDA_TRY(launch_conv_gemm(ma, mw, mo, g, block_n, num_sms(), stream));
+  // Residual through TMA (warp 3 prefetches each 128 x 64 residual tile into shared memory) whenever
+  // the residual rows of a tile are one box of a strided row view:
+  //   row(t) = sample*rows_per_sample + t*step + off  ==  view row (sample, t), column off*ld + c
+  // with the view's rows `step*ld` elements long (strided layout: off < step), or rows shifted by
+  // `off` (step == 1).  Other maps (flat tiles split over samples, bounds-checked rows) keep the
+  // register path.
+  CUtensorMap mr = ma;
+  g.res_tma = 0;
+  if (d->res && !d->res_check_rows && d->out && (d->per_sample_tiles || d->res_sample_div == 0) &&
+      d->res_row_step >= 1 && (d->res_row_step == 1 || d->res_row_off < d->res_row_step)) {
+    const uint64_t step = d->res_row_step, ld = d->res_ld;
+    const uint64_t r_samples = d->per_sample_tiles ? d->samples : 1;
+    uint64_t view_rows, col_off, row_off;
+    if (step == 1) {
+      view_rows = d->per_sample_tiles ? (uint64_t)d->res_rows_per_sample
+                                      : (uint64_t)d->out_rows + d->res_row_off;
+      col_off = 0;
+      row_off = d->res_row_off;
+    } else {
+      view_rows = d->per_sample_tiles ? (uint64_t)d->res_rows_per_sample / step
+                                      : (uint64_t)d->out_rows;
+      col_off = (uint64_t)d->res_row_off * ld;
+      row_off = 0;
+    }
+    const uint64_t inner = step * ld;
+    const uint64_t sample_stride = d->per_sample_tiles ? (uint64_t)d->res_rows_per_sample * ld
+                                                       : view_rows * inner;
+    uint64_t r_plane = (uint64_t)d->res_plane_stride;
+    if (g.res_planes == 1 || r_plane == 0) r_plane = r_samples * sample_stride;
+    if (row_off < (1u << 30) && view_rows > 0 &&
+        make_map_4d(&mr, d->res, inner, view_rows, inner, r_samples, sample_stride, g.res_planes,
+                    r_plane, kBlockM) == VP3D_OK) {
+      g.res_tma = 1;
+      g.res_tma_col_off = (int)col_off;
+      g.res_tma_row_off = (int)row_off;
+    }
+  }
+  CUDA_TRY(launch_conv_gemm(ma, mw, mo, mr, g, block_n, num_sms(), stream));
   return VP3D_OK;
 }
 
@@ -491,7 +529,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   // Per-layer operand precision.  index 0 = expand, 1..nb = residual blocks, nb+1 = shrink.
   //   bf16   : every GEMM single-plane bf16.
   //   bf16x3 : every GEMM split-bf16 (3 MMAs per product).
-  //   mixed  : the residual stream X keeps hi+lo planes (skip path exact); GEMMs holding < 8% of
+  //   mixed  : the residual stream X keeps hi+lo planes (skip path exact); GEMMs holding < 3% of
   //            the forward FLOPs (expand, shrink, the narrow tail blocks) run split-bf16, the
   //            FLOP-dominant blocks run plain bf16 on the hi plane.
   bool x3[VP3D_MAX_WIDTHS + 1];
@@ -504,7 +542,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     for (int i = 0; i <= p->nb + 1; ++i) {
       if (p->cfg.precision == VP3D_PRECISION_BF16) x3[i] = false;
       else if (p->cfg.precision == VP3D_PRECISION_BF16X3) x3[i] = true;
-      else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.08 * total);
+      else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.03 * total);
     }
   }
 
@@ -587,8 +625,10 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       d.res_rows_per_sample = 0; d.res_row_step = fw[i];
       d.res_row_off = fw[i] / 2 + p->shift_str[i]; d.res_sample_div = 0;
     } else {
+      // per-sample tiles: the residual rows of a tile are then one TMA box of the block input
+      d.samples = N; d.a_rows = Lout; d.per_sample_tiles = 1; d.out_rows = Lout;
       d.res_rows_per_sample = Lin; d.res_row_step = 1;
-      d.res_row_off = p->pad[i] + p->shift_dil[i]; d.res_sample_div = Lout;
+      d.res_row_off = p->pad[i] + p->shift_dil[i]; d.res_sample_div = 0;
     }
     d.out = xb[cur ^ 1]; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
     VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));

@@ -4,6 +4,8 @@
 //   warp 0 lane 0 : TMA producer  (A tile 128x64 bf16 + W tile BLOCK_Nx64 bf16 per k-block)
 //   warp 1 lane 0 : tcgen05.mma issuer (4 x K=16 MMAs per k-block, accumulator in TMEM)
 //   warp 2        : TMEM allocator / deallocator
+//   warp 3 lane 0 : residual producer (RES variant): TMA-loads the 128x64 residual tile of every
+//                   64-column store block into shared memory ahead of the epilogue
 //   warps 4..7    : epilogue: tcgen05.ld -> BN affine / ReLU / residual / batch sums in registers
 //                   -> bf16 pack into a SWIZZLE_128B staging tile in shared memory -> TMA store
 //                   (coalesced 128-byte rows, clipped at the tensor edge by the tensor map)
@@ -13,17 +15,21 @@
 
 namespace vp3d {
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RES>
 struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  // the RES variant trades one pipeline stage for three residual landing tiles
+  static constexpr int kStages = RES ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 5))
+                                     : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr uint32_t kStoreBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 staging tile
-  static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
-  // pipeline stages + 2 staging tiles + barriers + 1 KiB alignment slack
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 2 * kStoreBytes + kBarBytes + 1024;
+  static constexpr uint32_t kTileBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 tile (16 KiB)
+  static constexpr int kResSlots = RES ? 3 : 0;
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 6) * 8 + 16;
+  // pipeline stages + 2 store staging tiles + residual tiles + barriers + 1 KiB alignment slack
+  static constexpr uint32_t kSmemBytes =
+      kStages * kStageBytes + (2 + kResSlots) * kTileBytes + kBarBytes + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
@@ -49,13 +55,33 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                "r"(d)
                : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
 
-template <int BLOCK_N>
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
+  v[0] += bf16_lo_to_f(u.x);
+  v[1] += bf16_hi_to_f(u.x);
+  v[2] += bf16_lo_to_f(u.y);
+  v[3] += bf16_hi_to_f(u.y);
+  v[4] += bf16_lo_to_f(u.z);
+  v[5] += bf16_hi_to_f(u.z);
+  v[6] += bf16_lo_to_f(u.w);
+  v[7] += bf16_hi_to_f(u.w);
+}
+
+template <int BLOCK_N, bool RES>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_out, const ConvGemmArgs p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                 const __grid_constant__ CUtensorMap tmap_out,
+                 const __grid_constant__ CUtensorMap tmap_res, const ConvGemmArgs p) {
+  using Cfg = GemmCfg<BLOCK_N, RES>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -66,12 +92,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + kStages * Cfg::kABytes;
   const uint32_t smem_store = base + kStages * Cfg::kStageBytes;  // 2 x 16 KiB, 1024-aligned
-  const uint32_t bar_base = smem_store + 2 * Cfg::kStoreBytes;
+  const uint32_t smem_res = smem_store + 2 * Cfg::kTileBytes;     // kResSlots x 16 KiB
+  const uint32_t bar_base = smem_res + Cfg::kResSlots * Cfg::kTileBytes;
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + kStages * 8;
   const uint32_t tfull_bar = bar_base + 2 * kStages * 8;
   const uint32_t tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t rfull_bar = tempty_bar + 16;   // 3 residual stages
+  const uint32_t rempty_bar = rfull_bar + 24;
+  const uint32_t tmem_slot = rempty_bar + 24;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
@@ -81,11 +110,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int m_tiles = p.dilated ? p.samples * p.tiles_per_sample : p.tiles_per_sample;
   const int total_tiles = m_tiles * p.n_tiles;
   const int k_iters = p.pairs * p.taps * p.kblocks_per_tap;
+  // residual stages: one plane -> three tiles in flight; two planes -> one (hi, lo) pair
+  const int res_stages = (p.res_planes == 2) ? 1 : 3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_out);
+    if (RES) tma_prefetch_desc(&tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -95,6 +127,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s * 8, 1);
       mbar_init(tempty_bar + s * 8, 128);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(rfull_bar + s * 8, 1);
+      mbar_init(rempty_bar + s * 8, 128);
     }
     fence_mbar_init();
   }
@@ -160,6 +196,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ residual producer
+    if (RES && lane == 0) {
+      uint32_t rs = 0, rphase = 0;
+      const uint32_t bytes = p.res_planes * Cfg::kTileBytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_blk, sample, row0;
+        tile_coords(p, tile, n_blk, sample, row0);
+        for (int sb = 0; sb < BLOCK_N / 64; ++sb) {
+          const int col = n_blk * BLOCK_N + sb * 64;
+          if (col < p.res_col_begin || col >= p.res_col_begin + p.res_cols) continue;
+          mbar_wait(rempty_bar + rs * 8, rphase ^ 1);
+          mbar_expect_tx(rfull_bar + rs * 8, bytes);
+          for (int pl = 0; pl < p.res_planes; ++pl)
+            tma_load_4d(&tmap_res, rfull_bar + rs * 8,
+                        smem_res + (rs * p.res_planes + pl) * Cfg::kTileBytes,
+                        col - p.res_col_begin + p.res_tma_col_off, row0 + p.res_tma_row_off, sample,
+                        pl);
+          if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
@@ -167,13 +225,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool store_leader = (threadIdx.x == 128);
     uint32_t acc = 0, acc_phase = 0;
     uint32_t store_seq = 0;
+    uint32_t rs = 0, rphase = 0;
     const bool do_relu = p.flags & kEpiRelu;
     const bool do_res = p.flags & kEpiResidual;
     const bool do_stats = p.flags & kEpiStats;
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
     const bool two_planes = p.out_planes == 2;
-    // swizzled staging address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
+    // swizzled tile address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
     const uint32_t stage_row = r_in_tile * 128;
     const uint32_t sw = r_in_tile & 7;
 
@@ -183,17 +242,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int t = row0 + r_in_tile;
       const bool valid = t < p.out_rows;
       const long long out_row = (long long)sample * p.out_rows + t;
-      long long res_row;
+      long long res_row = 0;
       bool res_ok = valid;
-      {
-        int rs = sample, rt = t;
+      if (!RES) {
+        int rsmp = sample, rt = t;
         if (!p.dilated && p.res_sample_div > 0) {
-          rs = t / p.res_sample_div;
-          rt = t - rs * p.res_sample_div;
+          rsmp = t / p.res_sample_div;
+          rt = t - rsmp * p.res_sample_div;
         }
         const long long in_sample = (long long)rt * p.res_row_step + p.res_row_off;
         if (p.res_check_rows && (in_sample < 0 || in_sample >= p.res_rows_per_sample)) res_ok = false;
-        res_row = (long long)rs * p.res_rows_per_sample + in_sample;
+        res_row = (long long)rsmp * p.res_rows_per_sample + in_sample;
       }
 
       mbar_wait(tfull_bar + acc * 8, acc_phase);
@@ -203,6 +262,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         const int half = chunk & 1;  // which 32-column half of the 64-column store block
+        const int c0 = n_blk * BLOCK_N + chunk * 32;
+        const int cb = c0 - half * 32;  // first column of the store block
+        const bool res_here = do_res && cb >= p.res_col_begin && cb < p.res_col_begin + p.res_cols;
         // staging tile for this store block: single plane -> double buffered; two planes -> tile 0
         // holds hi, tile 1 holds lo and the previous store must have been read out first.
         const uint32_t buf = two_planes ? 0u : (store_seq & 1u);
@@ -216,7 +278,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t raw[32];
         tmem_ld_32x32(t_addr + chunk * 32, raw);
         tmem_ld_wait();
-        const int c0 = n_blk * BLOCK_N + chunk * 32;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -236,24 +297,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-        if (do_res && res_ok && c0 >= p.res_col_begin && c0 < p.res_col_begin + p.res_cols) {
+        if (RES) {
+          if (res_here) {
+            if (half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // residual tile(s) have landed
+            for (int pl = 0; pl < p.res_planes; ++pl) {
+              const uint32_t src = smem_res + (rs * p.res_planes + pl) * Cfg::kTileBytes + stage_row;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
+            }
+            if (half == 1) {
+              mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the residual stage
+              if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
+            }
+          }
+        } else if (res_here && res_ok) {
           const __nv_bfloat16* rp = p.res + res_row * p.res_ld + (c0 - p.res_col_begin);
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) {
             if (pl < p.res_planes) {
               const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(r4 + q);
-                v[q * 8 + 0] += bf16_lo_to_f(u.x);
-                v[q * 8 + 1] += bf16_hi_to_f(u.x);
-                v[q * 8 + 2] += bf16_lo_to_f(u.y);
-                v[q * 8 + 3] += bf16_hi_to_f(u.y);
-                v[q * 8 + 4] += bf16_lo_to_f(u.z);
-                v[q * 8 + 5] += bf16_hi_to_f(u.z);
-                v[q * 8 + 6] += bf16_lo_to_f(u.w);
-                v[q * 8 + 7] += bf16_hi_to_f(u.w);
-              }
+              for (int q = 0; q < 4; ++q) add_bf16x8(v + q * 8, __ldg(r4 + q));
             }
           }
         }
@@ -268,7 +333,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint32_t hi[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          const uint32_t dst = smem_store + buf * Cfg::kStoreBytes + stage_row;
+          const uint32_t dst = smem_store + buf * Cfg::kTileBytes + stage_row;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             st_shared_v4(dst + (((half * 4 + q) ^ sw) << 4), hi[4 * q], hi[4 * q + 1],
@@ -281,7 +346,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const float r1 = v[2 * j + 1] - bf16_hi_to_f(hi[j]);
               lo[j] = pack_bf16x2(r0, r1);
             }
-            const uint32_t dst_lo = smem_store + Cfg::kStoreBytes + stage_row;
+            const uint32_t dst_lo = smem_store + Cfg::kTileBytes + stage_row;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               st_shared_v4(dst_lo + (((half * 4 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1],
@@ -291,10 +356,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
             epi_bar_sync();
             if (store_leader) {
-              const int col = n_blk * BLOCK_N + (chunk - 1) * 32;
-              tma_store_4d(&tmap_out, smem_store + buf * Cfg::kStoreBytes, col, row0, sample, 0);
+              tma_store_4d(&tmap_out, smem_store + buf * Cfg::kTileBytes, cb, row0, sample, 0);
               if (two_planes)
-                tma_store_4d(&tmap_out, smem_store + Cfg::kStoreBytes, col, row0, sample, 1);
+                tma_store_4d(&tmap_out, smem_store + Cfg::kTileBytes, cb, row0, sample, 1);
               tma_store_commit();
             }
             ++store_seq;
@@ -344,14 +408,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RES>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                               const CUtensorMap& tmap_out, const ConvGemmArgs& args, int num_sms,
-                               cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                               const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                               const ConvGemmArgs& args, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -361,18 +425,28 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   const int total = m_tiles * args.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, args);
+  conv_gemm_kernel<BLOCK_N, RES>
+      <<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, args);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                             const CUtensorMap& tmap_out, const ConvGemmArgs& args, int block_n,
-                             int num_sms, cudaStream_t stream) {
+                             const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                             const ConvGemmArgs& args, int block_n, int num_sms,
+                             cudaStream_t stream) {
+  const bool res = args.res_tma != 0;
   switch (block_n) {
-    case 256: return launch_impl<256>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
-    case 128: return launch_impl<128>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
-    case 64: return launch_impl<64>(tmap_a, tmap_w, tmap_out, args, num_sms, stream);
-    default: return cudaErrorInvalidValue;
+    case 256:
+      return res ? launch_impl<256, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
+                 : launch_impl<256, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+    case 128:
+      return res ? launch_impl<128, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
+                 : launch_impl<128, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+    case 64:
+      return res ? launch_impl<64, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
+                 : launch_impl<64, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+    default:
+      return cudaErrorInvalidValue;
   }
 }
 

@@ -64,6 +64,9 @@ struct ConvGemmArgs {
   int res_col_begin;            // residual is added only to output columns [res_col_begin, +res_cols)
   int res_cols;                 //   reading residual column (col - res_col_begin)   (dgrad skip path)
   int res_check_rows;           // 1: skip rows whose mapped in-sample row falls outside [0, res_rows_per_sample)
+  int res_tma;                  // 1: residual tiles are TMA-loaded by warp 3 through tmap_res (RES variant)
+  int res_tma_col_off;          //   column offset inside the residual map's row view
+  int res_tma_row_off;          //   row offset (added to the tile's first row)
   __nv_bfloat16* out;          // bf16 output plane 0, [samples*out_rows, out_ld]
   long long out_plane_stride;
   int out_planes;              // 1 or 2
@@ -77,8 +80,11 @@ struct ConvGemmArgs {
 // Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);
 // tmap_out: 4-D (channel, row, sample, plane) over the bf16 output, box (64, 128, 1, 1) (ignored —
 // pass any valid map — when the launch writes fp32).
+// tmap_res: 4-D (channel, row, sample, plane) over the residual's row view, box (64, 128, 1, 1); used
+// only when args.res_tma is set.
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
-                             const CUtensorMap& tmap_out, const ConvGemmArgs& args, int block_n,
-                             int num_sms, cudaStream_t stream);
+                             const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
+                             const ConvGemmArgs& args, int block_n, int num_sms,
+                             cudaStream_t stream);
 
 }  // namespace vp3d

@@ -50,39 +50,45 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   return cudaGetLastError();
 }
 
-// One thread per output element pair is plenty: weights are repacked once per optimizer step at most.
+// One thread per (co, k) position of the padded slab; the thread walks the taps, so the fp32 reads of
+// a warp cover one contiguous span of Conv1d.weight and each tap slab receives a coalesced bf16 row.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                         int planes, int c_out, int c_in, int taps, int n_pad,
-                                        int k_pad, int merge_taps) {
-  const int taps_out = merge_taps ? 1 : taps;
-  const long long plane_elems = (long long)taps_out * n_pad * k_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane_elems;
+                                        int k_pad, int merged) {
+  const long long slab = (long long)n_pad * k_pad;
+  const long long plane_elems = (merged ? 1 : taps) * slab;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < slab;
        i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % k_pad);
-    const int co = (int)((i / k_pad) % n_pad);
-    const int tp = (int)(i / ((long long)k_pad * n_pad));
-    float v = 0.0f;
-    if (co < c_out) {
-      if (merge_taps) {
-        if (k < taps * c_in) {
-          const int tap = k / c_in, ci = k - tap * c_in;
-          v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
-        }
-      } else if (k < c_in) {
-        v = __ldg(w + ((long long)co * c_in + k) * taps + tp);
+    const int co = (int)(i / k_pad);
+    if (merged) {
+      float v = 0.0f;
+      if (co < c_out && k < taps * c_in) {
+        const int tap = k / c_in, ci = k - tap * c_in;
+        v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
+      }
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      out[i] = hi;
+      if (planes == 2) out[plane_elems + i] = lo;
+    } else {
+      const bool in = co < c_out && k < c_in;
+      const float* src = w + ((long long)co * c_in + k) * taps;
+      for (int tap = 0; tap < taps; ++tap) {
+        const float v = in ? __ldg(src + tap) : 0.0f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        out[tap * slab + i] = hi;
+        if (planes == 2) out[plane_elems + tap * slab + i] = lo;
       }
     }
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    out[i] = hi;
-    if (planes == 2) out[plane_elems + i] = lo;
   }
 }
 
 cudaError_t launch_pack_conv_weight(const float* w, __nv_bfloat16* out, int planes, int c_out,
                                     int c_in, int taps, int n_pad, int k_pad, int merge_taps,
                                     cudaStream_t stream) {
-  const long long total = (long long)(merge_taps ? 1 : taps) * n_pad * k_pad;
+  const long long total = (long long)n_pad * k_pad;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;

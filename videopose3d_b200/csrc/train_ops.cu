@@ -91,32 +91,38 @@ __device__ __forceinline__ long long map_row(const RowMap& m, long long r) {
   return r * m.step + m.off;
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
-                                __nv_bfloat16* __restrict__ x, long long x_plane, int planes,
-                                long long rows, int c, const float* __restrict__ scale,
-                                const float* __restrict__ shift, DropoutCfg drop,
-                                const __nv_bfloat16* __restrict__ res, long long res_plane,
-                                RowMap map) {
-  const int groups = c >> 3;
-  const long long total = rows * groups;
+// Thread layout shared by the row-streaming kernels: 256 threads = 8 column groups (8 channels each,
+// 64 channels per block) x 32 row lanes; a block walks kRowsPerBlock rows.  Per-channel vectors are
+// loaded once into registers and reused for every row the thread touches; a warp's access is 4 rows
+// x 128 contiguous bytes.
+constexpr int kRowsPerBlock = 256;
+
+__device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
+                __nv_bfloat16* __restrict__ x, long long x_plane, int planes, long long rows, int c,
+                const float* __restrict__ scale, const float* __restrict__ shift, DropoutCfg drop,
+                const __nv_bfloat16* __restrict__ res, long long res_plane, RowMap map) {
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
+  const long long r_end = min(rows, r_begin + kRowsPerBlock);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const long long r = i / groups;
-    const int c0 = g * 8;
+  float sc[8], sh[8];
+  load_vec8(scale + c0, sc);
+  load_vec8(shift + c0, sh);
+  for (long long r = r_begin + rl; r < r_end; r += 32) {
     float v[8];
     load8(z + r * c + c0, z_plane, planes, v);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
-    v[0] = fmaxf(fmaf(v[0], s0.x, b0.x), 0.f); v[1] = fmaxf(fmaf(v[1], s0.y, b0.y), 0.f);
-    v[2] = fmaxf(fmaf(v[2], s0.z, b0.z), 0.f); v[3] = fmaxf(fmaf(v[3], s0.w, b0.w), 0.f);
-    v[4] = fmaxf(fmaf(v[4], s1.x, b1.x), 0.f); v[5] = fmaxf(fmaf(v[5], s1.y, b1.y), 0.f);
-    v[6] = fmaxf(fmaf(v[6], s1.z, b1.z), 0.f); v[7] = fmaxf(fmaf(v[7], s1.w, b1.w), 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.0f);
     if (do_drop) {
       float m[8];
       dropout_keep8(drop, r * c + c0, thresh, inv_keep, m);
@@ -133,11 +139,11 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z
   }
 }
 
-// dY for 8 channels of one row.
+// dY for 8 channels of one row: dY = g * dropmask/(1-p) * [z*scale+shift > 0].
 __device__ __forceinline__ void dy8(const __nv_bfloat16* g, long long g_plane,
                                     const __nv_bfloat16* z, long long z_plane, int planes,
-                                    long long r, int c, int c0, const float* scale,
-                                    const float* shift, const DropoutCfg& drop, bool do_drop,
+                                    long long r, int c, int c0, const float (&sc)[8],
+                                    const float (&sh)[8], const DropoutCfg& drop, bool do_drop,
                                     uint32_t thresh, float inv_keep, float (&dy)[8],
                                     float (&zv)[8]) {
   float gv[8];
@@ -147,50 +153,48 @@ __device__ __forceinline__ void dy8(const __nv_bfloat16* g, long long g_plane,
   if (do_drop) dropout_keep8(drop, r * c + c0, thresh, inv_keep, m);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float y = fmaf(zv[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
-    float d = y > 0.0f ? gv[j] : 0.0f;
+    float d = fmaf(zv[j], sc[j], sh[j]) > 0.0f ? gv[j] : 0.0f;
     if (do_drop) d *= m[j];
     dy[j] = d;
   }
 }
 
-// block = 256 threads = 8 column groups (64 channels) x 32 row lanes; grid = (c/64, row chunks)
-constexpr int kRedRowsPerBlock = 512;
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
-                                     const __nv_bfloat16* __restrict__ z, long long z_plane,
-                                     int planes, long long rows, int c,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     DropoutCfg drop, float* __restrict__ sums) {
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
+                     const __nv_bfloat16* __restrict__ z, long long z_plane, int planes,
+                     long long rows, int c, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, DropoutCfg drop, float* __restrict__ sums) {
   __shared__ float sm[2][8][64];
   const int cg = threadIdx.x & 7;
   const int rl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * 64 + cg * 8;
-  const long long r_begin = (long long)blockIdx.y * kRedRowsPerBlock;
-  const long long r_end = min(rows, r_begin + kRedRowsPerBlock);
+  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
+  const long long r_end = min(rows, r_begin + kRowsPerBlock);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
-  float s1[8], s2[8], mu[8], is[8];
+  float s1[8], s2[8], mu[8], sc[8], sh[8];
+  load_vec8(mean + c0, mu);
+  load_vec8(scale + c0, sc);
+  load_vec8(shift + c0, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s1[j] = s2[j] = 0.0f;
-    mu[j] = __ldg(mean + c0 + j);
-    is[j] = __ldg(invstd + c0 + j);
-  }
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.0f;
   for (long long r = r_begin + rl; r < r_end; r += 32) {
     float dy[8], zv[8];
-    dy8(g, g_plane, z, z_plane, planes, r, c, c0, scale, shift, drop, do_drop, thresh, inv_keep, dy,
-        zv);
+    dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s1[j] += dy[j];
-      s2[j] += dy[j] * (zv[j] - mu[j]) * is[j];
+      s2[j] += dy[j] * (zv[j] - mu[j]);  // invstd factored out of the sum
     }
   }
+  float is[8];
+  load_vec8(invstd + c0, is);
   // the 4 row lanes sharing a warp: lanes differ in bits 3,4
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
+    s2[j] *= is[j];
     s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
     s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
     s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
@@ -214,41 +218,51 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long l
   }
 }
 
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
-                                    const __nv_bfloat16* __restrict__ z, long long z_plane,
-                                    __nv_bfloat16* __restrict__ dz, long long dz_plane, int planes,
-                                    long long rows, int c, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, DropoutCfg drop,
-                                    const float* __restrict__ sums, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
-  const int groups = c >> 3;
-  const long long total = rows * groups;
+// dz = scale*(dY - s1/n - xhat*s2/n) = scale*dY + B*z + D with per-channel
+// B = -scale*invstd*s2/n,  D = -scale*s1/n - B*mean.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
+                    const __nv_bfloat16* __restrict__ z, long long z_plane,
+                    __nv_bfloat16* __restrict__ dz, long long dz_plane, int planes, long long rows,
+                    int c, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    DropoutCfg drop, const float* __restrict__ sums, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
+  const long long r_end = min(rows, r_begin + kRowsPerBlock);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
   const float inv_n = 1.0f / (float)rows;
-  if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
-      if (dbeta) dbeta[i] = sums[i];
-      if (dgamma) dgamma[i] = sums[c + i];
+  float sc[8], sh[8], B[8], D[8];
+  {
+    float mu[8], is[8], s1[8], s2[8];
+    load_vec8(scale + c0, sc);
+    load_vec8(shift + c0, sh);
+    load_vec8(mean + c0, mu);
+    load_vec8(invstd + c0, is);
+    load_vec8(sums + c0, s1);
+    load_vec8(sums + c + c0, s2);
+    if (blockIdx.y == 0 && rl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (dbeta) dbeta[c0 + j] = s1[j];
+        if (dgamma) dgamma[c0 + j] = s2[j];
+      }
     }
-  }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int gq = (int)(i % groups);
-    const long long r = i / groups;
-    const int c0 = gq * 8;
-    float dy[8], zv[8], o[8];
-    dy8(g, g_plane, z, z_plane, planes, r, c, c0, scale, shift, drop, do_drop, thresh, inv_keep, dy,
-        zv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (zv[j] - __ldg(mean + c0 + j)) * __ldg(invstd + c0 + j);
-      // scale = gamma * invstd
-      o[j] = __ldg(scale + c0 + j) *
-             (dy[j] - __ldg(sums + c0 + j) * inv_n - xh * __ldg(sums + c + c0 + j) * inv_n);
+      B[j] = -sc[j] * is[j] * s2[j] * inv_n;
+      D[j] = -sc[j] * s1[j] * inv_n - B[j] * mu[j];
     }
+  }
+  for (long long r = r_begin + rl; r < r_end; r += 32) {
+    float dy[8], zv[8], o[8];
+    dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], dy[j], fmaf(B[j], zv[j], D[j]));
     store8(dz + r * c + c0, dz_plane, planes, o);
   }
 }
@@ -264,20 +278,36 @@ __global__ void col_sum_f32_kernel(const float* __restrict__ x, long long rows, 
   }
 }
 
-__global__ void pack_conv_weight_t_kernel(const float* __restrict__ w,
-                                          __nv_bfloat16* __restrict__ out, int planes, int c_out,
-                                          int c_in, int taps, int n_pad, int k_pad) {
+// w fp32 (c_out, c_in, taps) -> out_t[pl][tap][ci][co] (rows n_pad = padded c_in, cols k_pad = padded
+// c_out).  32 x 32 (co, ci) tiles go through shared memory so that both the reads (ci fastest) and
+// the writes (co fastest) are coalesced.  Padding entries are written as zeros.
+__global__ void __launch_bounds__(256)
+pack_conv_weight_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int planes,
+                          int c_out, int c_in, int taps, int n_pad, int k_pad) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const long long plane_elems = (long long)taps * n_pad * k_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane_elems;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % k_pad);
-    const int ci = (int)((i / k_pad) % n_pad);
-    const int tap = (int)(i / ((long long)k_pad * n_pad));
-    float v = 0.0f;
-    if (co < c_out && ci < c_in) v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[i] = hi;
-    if (planes == 2) out[plane_elems + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  for (int tap = 0; tap < taps; ++tap) {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int co = co0 + j, ci = ci0 + tx;
+      sm[j][tx] = (co < c_out && ci < c_in) ? __ldg(w + ((long long)co * c_in + ci) * taps + tap)
+                                            : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int ci = ci0 + j, co = co0 + tx;
+      if (ci < n_pad && co < k_pad) {
+        const float v = sm[tx][j];
+        const long long o = ((long long)tap * n_pad + ci) * k_pad + co;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        out[o] = hi;
+        if (planes == 2) out[plane_elems + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -305,8 +335,9 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bflo
                             const float* shift, DropoutCfg drop, const __nv_bfloat16* res,
                             long long res_plane, RowMap map, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  bn_apply_kernel<<<grid_for(rows * (c >> 3), 256), 256, 0, stream>>>(
-      z, z_plane, x, x_plane, planes, rows, c, scale, shift, drop, res, res_plane, map);
+  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  bn_apply_kernel<<<grid, 256, 0, stream>>>(z, z_plane, x, x_plane, planes, rows, c, scale, shift,
+                                            drop, res, res_plane, map);
   return cudaGetLastError();
 }
 
@@ -316,7 +347,7 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, cons
                                  const float* invstd, DropoutCfg drop, float* sums,
                                  cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  dim3 grid(c / 64, (unsigned)((rows + kRedRowsPerBlock - 1) / kRedRowsPerBlock));
+  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
                                                  shift, mean, invstd, drop, sums);
   return cudaGetLastError();
@@ -328,9 +359,10 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
                                 const float* mean, const float* invstd, DropoutCfg drop,
                                 const float* sums, float* dgamma, float* dbeta, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  bn_bwd_apply_kernel<<<grid_for(rows * (c >> 3), 256), 256, 0, stream>>>(
-      g, g_plane, z, z_plane, dz, dz_plane, planes, rows, c, scale, shift, mean, invstd, drop, sums,
-      dgamma, dbeta);
+  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, dz, dz_plane, planes, rows,
+                                                c, scale, shift, mean, invstd, drop, sums, dgamma,
+                                                dbeta);
   return cudaGetLastError();
 }
 
@@ -343,9 +375,9 @@ cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out
 
 cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
                                       int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream) {
-  const long long total = (long long)taps * n_pad * k_pad;
-  pack_conv_weight_t_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, out, planes, c_out, c_in,
-                                                                      taps, n_pad, k_pad);
+  dim3 grid((n_pad + 31) / 32, (k_pad + 31) / 32);
+  pack_conv_weight_t_kernel<<<grid, 256, 0, stream>>>(w, out, planes, c_out, c_in, taps, n_pad,
+                                                      k_pad);
   return cudaGetLastError();
 }
 

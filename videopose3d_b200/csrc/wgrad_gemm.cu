@@ -208,22 +208,24 @@ cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tma
   return cudaGetLastError();
 }
 
-// grad layout (c_out, c_in, taps_out): consecutive threads walk ci (and taps) of one co.
+// One thread per (co, ci): partial reads are coalesced along ci for every (split, tap); the taps of
+// one (co, ci) are written as one contiguous run of the (c_out, c_in, taps) gradient layout.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                     int splits, int taps_p, int m_pad, int n_pad, int c_out, int c_in,
                                     int taps_out, int merged) {
-  const long long total = (long long)c_out * c_in * taps_out;
+  const long long total = (long long)c_out * c_in;
   const long long split_stride = (long long)taps_p * m_pad * n_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % taps_out);
-    const int ci = (int)((i / taps_out) % c_in);
-    const int co = (int)(i / ((long long)taps_out * c_in));
-    const long long src = merged ? ((long long)co * n_pad + tap * c_in + ci)
-                                 : (((long long)tap * m_pad + co) * n_pad + ci);
-    float s = 0.0f;
-    for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + sp * split_stride + src);
-    grad[i] = s;
+    const int ci = (int)(i % c_in);
+    const int co = (int)(i / c_in);
+    for (int tap = 0; tap < taps_out; ++tap) {
+      const long long src = merged ? ((long long)co * n_pad + tap * c_in + ci)
+                                   : (((long long)tap * m_pad + co) * n_pad + ci);
+      float s = 0.0f;
+      for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + sp * split_stride + src);
+      grad[i * taps_out + tap] = s;
+    }
   }
 }
 }  // namespace
@@ -241,7 +243,7 @@ cudaError_t launch_wgrad_gemm(const CUtensorMap& tmap_dz, const CUtensorMap& tma
 cudaError_t launch_wgrad_reduce(const float* partial, float* grad, int splits, int taps_p, int m_pad,
                                 int n_pad, int c_out, int c_in, int taps_out, int merged,
                                 cudaStream_t stream) {
-  const long long total = (long long)c_out * c_in * taps_out;
+  const long long total = (long long)c_out * c_in;
   if (total <= 0) return cudaSuccess;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

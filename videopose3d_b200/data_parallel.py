@@ -59,8 +59,9 @@ class GradientReducer:
         return names, spans, stage_spans, off
 
     def attach(self, module):
-        module._grad_reducer = self
-        return module
+        """Route `module`'s training backward through this reducer; returns the reducer."""
+        object.__setattr__(module, "_grad_reducer", self)
+        return self
 
     # ---------------------------------------------------------------- collective
     def reduce_flat(self, flat):
