@@ -86,7 +86,7 @@ def _conv_cl(x, w, stride=1, dilation=1):
     return y
 
 
-def _bn_cl(x, prefix, sd, training, momentum, new_stats):
+def _bn_cl(x, prefix, sd, training, momentum, new_stats, probe=None):
     g, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
     if training:
         flat = x.reshape(-1, x.shape[-1])
@@ -100,11 +100,14 @@ def _bn_cl(x, prefix, sd, training, momentum, new_stats):
             new_stats[prefix + ".num_batches_tracked"] = sd[prefix + ".num_batches_tracked"] + 1
     else:
         mean, var = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
-    return (x - mean) / np.sqrt(var + EPS) * g + b
+    y = (x - mean) / np.sqrt(var + EPS) * g + b
+    if probe is not None:  # distance of the closest pre-activation to the ReLU kink
+        probe["min_abs_preact"] = min(probe.get("min_abs_preact", np.inf), float(np.abs(y).min()))
+    return y
 
 
 def forward_numpy(sd, x, filter_widths, causal=False, dense=False, strided=False, training=False,
-                  momentum=0.1, dtype=np.float64, return_new_stats=False, collect=None):
+                  momentum=0.1, dtype=np.float64, return_new_stats=False, collect=None, probe=None):
     """sd: state_dict (numpy or torch values); x: (N, T, J, F).  Dropout is the identity here
     (eval, or training with p = 0).  Returns (N, T_out, J_out, 3) [and the updated BN buffers]."""
     sd = state_dict_to_numpy(sd, dtype)
@@ -117,7 +120,7 @@ def forward_numpy(sd, x, filter_widths, causal=False, dense=False, strided=False
     new_stats = {} if return_new_stats else None
 
     h = _conv_cl(h, sd["expand_conv.weight"], stride=fw[0] if strided else 1)
-    h = np.maximum(_bn_cl(h, "expand_bn", sd, training, momentum, new_stats), 0)   # :127 / :188
+    h = np.maximum(_bn_cl(h, "expand_bn", sd, training, momentum, new_stats, probe), 0)   # :127 / :188
     if collect is not None:
         collect.append(h)
     for i in range(len(fw) - 1):
@@ -130,11 +133,11 @@ def forward_numpy(sd, x, filter_widths, causal=False, dense=False, strided=False
             pad, sh = a["pad"][i + 1], a["shift"][i + 1]
             res = h[:, pad + sh: h.shape[1] - pad + sh, :]                         # :130-132
             z = _conv_cl(h, sd[f"layers_conv.{2 * i}.weight"], dilation=a["dilation"][i + 1])
-        z = np.maximum(_bn_cl(z, f"layers_bn.{2 * i}", sd, training, momentum, new_stats), 0)
+        z = np.maximum(_bn_cl(z, f"layers_bn.{2 * i}", sd, training, momentum, new_stats, probe), 0)
         if collect is not None:
             collect.append(z)
         z = _conv_cl(z, sd[f"layers_conv.{2 * i + 1}.weight"])
-        z = np.maximum(_bn_cl(z, f"layers_bn.{2 * i + 1}", sd, training, momentum, new_stats), 0)
+        z = np.maximum(_bn_cl(z, f"layers_bn.{2 * i + 1}", sd, training, momentum, new_stats, probe), 0)
         h = res + z                                                                  # :135 / :194
         if collect is not None:
             collect.append(h)

@@ -46,6 +46,12 @@ CASES = {
     "tm_3_c64": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3], C=64, N=2, T=9),
     "tm_333_c64_train": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=4, T=30,
                              train=True, momentum=0.07),
+    "tm_333_c128_train": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=128, N=3, T=34,
+                              train=True, momentum=0.1),
+    "tm_35_c128_train_causal": dict(cls="TemporalModel", J=16, F=2, Jout=16, fw=[3, 5], C=128, N=3,
+                                    T=24, train=True, momentum=0.1, causal=True),
+    "tm_33_c64_dense_train": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3], C=64, N=4, T=16,
+                                  train=True, momentum=0.1, dense=True),
     "opt_333_c64_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64,
                               N=6, T=27, train=True, momentum=0.1),
     "opt_333_c128_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=128,
@@ -71,12 +77,25 @@ def build_case(name, cfg):
     seed = sum(ord(c) for c in name)  # stable across runs
     causal = bool(cfg.get("causal", False))
     dense = bool(cfg.get("dense", False))
+    tries = 0
     while True:
+        tries += 1
+        assert tries <= 400, f"{name}: no seed keeps every pre-activation away from the ReLU kink"
         sd = orc.make_state_dict(cfg["J"], cfg["F"], cfg["Jout"], cfg["fw"], cfg["C"], dense=dense,
                                  seed=seed)
         x = orc.make_input(cfg["N"], cfg["T"], cfg["J"], cfg["F"], seed=seed + 1)
-        if not (cfg.get("train") and cfg["cls"] == "TemporalModelOptimized1f"):
+        if not cfg.get("train"):
             break
+        if cfg["cls"] == "TemporalModel":
+            probe = {}
+            orc.forward_numpy(sd, x.numpy(), cfg["fw"], causal=causal, dense=dense, training=True,
+                              momentum=cfg["momentum"], probe=probe)
+            # the dilated fixtures hold far more activations, so the margin is 5e-5 (still 5x the
+            # split-bf16 rounding error) instead of 2e-4
+            if probe["min_abs_preact"] >= 5e-5:
+                break
+            seed += 1000
+            continue
         # Gradient parity at 1e-3 is only well-posed away from ReLU kinks: a pre-activation within
         # rounding error of zero flips its mask and moves gradients by O(1/rows).  Keep seeds whose
         # smallest |pre-activation| is >= 2e-4 (checked with the float64 emulation).

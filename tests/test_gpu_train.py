@@ -16,11 +16,15 @@ import videopose3d_b200 as vp
 pytestmark = pytest.mark.gpu
 
 TRAIN_CASES = [n for n in golden_names() if n.startswith("opt") and "train" in n]
+TM_TRAIN_CASES = [n for n in golden_names() if n.startswith("tm") and "train" in n]
 
 
 def _build(meta, sd, dev, precision, dropout=0.0):
-    m = vp.TemporalModelOptimized1f(meta["J"], meta["F"], meta["Jout"], filter_widths=meta["fw"],
-                                    causal=meta["causal"], dropout=dropout, channels=meta["C"])
+    kw = dict(filter_widths=meta["fw"], causal=meta["causal"], dropout=dropout, channels=meta["C"])
+    if meta["cls"] == "TemporalModel":
+        m = vp.TemporalModel(meta["J"], meta["F"], meta["Jout"], dense=meta["dense"], **kw)
+    else:
+        m = vp.TemporalModelOptimized1f(meta["J"], meta["F"], meta["Jout"], **kw)
     m.load_state_dict(sd)
     m = m.to(dev).train().set_train_precision(precision)
     m.set_bn_momentum(meta.get("momentum", 0.1))
@@ -60,7 +64,7 @@ def test_bf16_train_step_matches_quantisation_aware_emulation(cuda_device, name)
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3)])
-@pytest.mark.parametrize("name", TRAIN_CASES)
+@pytest.mark.parametrize("name", TRAIN_CASES + TM_TRAIN_CASES)
 def test_train_step_matches_reference(cuda_device, name, precision, tol):
     meta, sd, x, y_ref, new = load_golden(name)
     m = _build(meta, sd, cuda_device, precision)
@@ -181,7 +185,17 @@ def test_cfg3_full_size_train_step(cuda_device):
     assert losses[-1] < losses[0], losses
 
 
-def test_temporal_model_train_raises_not_silently_falls_back(cuda_device):
-    m = vp.TemporalModel(17, 2, 17, [3, 3, 3], channels=64).to(cuda_device).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(2, 27, 17, 2, device=cuda_device))
+@pytest.mark.parametrize("name", TM_TRAIN_CASES)
+def test_dilated_train_bf16_runs_and_is_close(cuda_device, name):
+    """TemporalModel (dilated) training in bf16 mode: forward within 5e-2 of the fp32 reference,
+    gradients finite and within 35 % (relative L2; ReLU-mask flips on a tiny batch, see
+    oracle/train_emulation.py) — the tight check is the bf16x3 case above."""
+    from oracle import train_emulation as emu
+    meta, sd, x, y_ref, new = load_golden(name)
+    m = _build(meta, sd, cuda_device, "bf16")
+    y = m(x.to(cuda_device))
+    assert _rel(y, y_ref) <= 5e-2
+    (y * torch.from_numpy(new["gy"]).to(cuda_device)).sum().backward()
+    for k, prm in m.named_parameters():
+        assert torch.isfinite(prm.grad).all(), k
+        assert emu.rel_l2(prm.grad, new["grad/" + k]) <= 0.35, k

@@ -205,11 +205,14 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   // register path.
   CUtensorMap mr = ma;
   g.res_tma = 0;
-  if (d->res && !d->res_check_rows && d->out && (d->per_sample_tiles || d->res_sample_div == 0) &&
+  // (per-sample maps zero-fill rows outside the sample, which is exactly what res_check_rows asks)
+  if (d->res && (!d->res_check_rows || (d->per_sample_tiles && d->res_row_step == 1)) && d->out &&
+      (d->per_sample_tiles || d->res_sample_div == 0) &&
       d->res_row_step >= 1 && (d->res_row_step == 1 || d->res_row_off < d->res_row_step)) {
     const uint64_t step = d->res_row_step, ld = d->res_ld;
     const uint64_t r_samples = d->per_sample_tiles ? d->samples : 1;
-    uint64_t view_rows, col_off, row_off;
+    uint64_t view_rows, col_off;
+    long long row_off;
     if (step == 1) {
       view_rows = d->per_sample_tiles ? (uint64_t)d->res_rows_per_sample
                                       : (uint64_t)d->out_rows + d->res_row_off;
@@ -226,7 +229,7 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
                                                        : view_rows * inner;
     uint64_t r_plane = (uint64_t)d->res_plane_stride;
     if (g.res_planes == 1 || r_plane == 0) r_plane = r_samples * sample_stride;
-    if (row_off < (1u << 30) && view_rows > 0 &&
+    if (view_rows > 0 &&
         make_map_4d(&mr, d->res, inner, view_rows, inner, r_samples, sample_stride, g.res_planes,
                     r_plane, kBlockM) == VP3D_OK) {
       g.res_tma = 1;
@@ -350,6 +353,8 @@ extern "C" __attribute__((visibility("default"))) void vp3d_plan_destroy(vp3d_pl
   if (p->d_y) cudaFree(p->d_y);
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  for (cudaEvent_t e : p->copy_events) cudaEventDestroy(e);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   if (p->train) train_state_destroy(p->train);
   delete p;
@@ -675,8 +680,41 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host(vp3
     CUDA_TRY(cudaMalloc(&p->d_ws, wb));
     p->d_ws_bytes = wb;
   }
-  CUDA_TRY(cudaMemcpyAsync(p->d_x, x_host, xb, cudaMemcpyHostToDevice, p->stream));
-  VP3D_TRY(vp3d_forward_eval(p, p->d_x, p->d_y, N, T, p->d_ws, p->d_ws_bytes, p->stream));
+  // Batch rows are independent in eval mode: split the batch into chunks so that the host->device
+  // copy of chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream).  PCIe moves
+  // 33.8 MB per 1024 x 243 batch, which is longer than the whole forward.
+  const int chunks = N >= 512 ? 4 : (N >= 128 ? 2 : 1);
+  if (chunks == 1) {
+    CUDA_TRY(cudaMemcpyAsync(p->d_x, x_host, xb, cudaMemcpyHostToDevice, p->stream));
+    VP3D_TRY(vp3d_forward_eval(p, p->d_x, p->d_y, N, T, p->d_ws, p->d_ws_bytes, p->stream));
+  } else {
+    if (!p->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    while ((int)p->copy_events.size() < chunks) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->copy_events.push_back(e);
+    }
+    const size_t x_row = (size_t)T * p->c_in_raw, y_row = (size_t)t_out * p->c_out_raw;
+    int launches = 0;
+    // the previous call's kernels may still read d_x: order the copies behind them
+    CUDA_TRY(cudaEventRecord(p->copy_events[0], p->stream));
+    CUDA_TRY(cudaStreamWaitEvent(p->copy_stream, p->copy_events[0], 0));
+    for (int c = 0; c < chunks; ++c) {
+      const int n0 = (int)((long long)N * c / chunks), n1 = (int)((long long)N * (c + 1) / chunks);
+      CUDA_TRY(cudaMemcpyAsync(p->d_x + n0 * x_row, x_host + n0 * x_row,
+                               (size_t)(n1 - n0) * x_row * sizeof(float), cudaMemcpyHostToDevice,
+                               p->copy_stream));
+      CUDA_TRY(cudaEventRecord(p->copy_events[c], p->copy_stream));
+    }
+    for (int c = 0; c < chunks; ++c) {
+      const int n0 = (int)((long long)N * c / chunks), n1 = (int)((long long)N * (c + 1) / chunks);
+      CUDA_TRY(cudaStreamWaitEvent(p->stream, p->copy_events[c], 0));
+      VP3D_TRY(vp3d_forward_eval(p, p->d_x + n0 * x_row, p->d_y + n0 * y_row, n1 - n0, T, p->d_ws,
+                                 p->d_ws_bytes, p->stream));
+      launches += p->last_launches;
+    }
+    p->last_launches = launches;
+  }
   CUDA_TRY(cudaMemcpyAsync(y_host, p->d_y, yb, cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return VP3D_OK;

@@ -74,6 +74,8 @@ struct vp3d_plan {
   void* d_ws = nullptr;
   size_t d_x_bytes = 0, d_y_bytes = 0, d_ws_bytes = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // host API: H2D chunks overlap the compute stream
+  std::vector<cudaEvent_t> copy_events;
   int last_launches = 0;
   // measurement hook: event pairs around one chosen launch of each forward
   int prof_launch = -1;

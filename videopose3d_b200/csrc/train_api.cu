@@ -12,8 +12,9 @@
 // data gradient G_prev = dZ * W^T through the same conv GEMM kernel on transposed weight packs,
 // with the skip-connection gradient added in the epilogue.
 //
-// Covered schedule: the strided layout (TemporalModelOptimized1f, the model run.py trains with by
-// default, run.py:172-175).  Training the dilated TemporalModel returns VP3D_ERR_UNSUPPORTED.
+// Both layouts are covered: strided (TemporalModelOptimized1f, the model run.py trains with by
+// default, run.py:172-175) and dilated (TemporalModel, run.py:176-180: per-sample tiles, transposed
+// convolution for the data gradient, per-sample reduction for the weight gradient).
 #include <stdio.h>
 
 #include "internal.cuh"
@@ -95,7 +96,8 @@ struct TrainLayout {
   long long rows[VP3D_MAX_WIDTHS] = {};  // rows[i] = N * L[i]
 };
 
-TrainLayout train_layout(const vp3d_plan* p, int N, const int* L) {
+TrainLayout train_layout(const vp3d_plan* p, int N, int T, const int* L) {
+  const bool strided = p->cfg.variant == VP3D_VARIANT_STRIDED;
   TrainLayout w;
   const size_t C = p->C, pl = p->planes;
   size_t off = 0;
@@ -105,7 +107,7 @@ TrainLayout train_layout(const vp3d_plan* p, int N, const int* L) {
     return o;
   };
   for (int i = 0; i <= p->nb; ++i) w.rows[i] = (long long)N * L[i];
-  w.a0 = take(pl * w.rows[0] * p->k0_pad * 2);
+  w.a0 = take(strided ? pl * w.rows[0] * p->k0_pad * 2 : pl * (size_t)N * T * p->c_in_pad * 2);
   w.z[0] = take(pl * w.rows[0] * C * 2);
   w.x[0] = take(pl * w.rows[0] * C * 2);
   for (int i = 1; i <= p->nb; ++i) {
@@ -123,51 +125,74 @@ TrainLayout train_layout(const vp3d_plan* p, int N, const int* L) {
   // wgrad partials: up to 8 splits x taps x C x max(C, k0_pad) fp32
   int max_taps = 1;
   for (int i = 1; i <= p->nb; ++i) max_taps = p->taps[i] > max_taps ? p->taps[i] : max_taps;
-  const size_t n_max = p->C > p->k0_pad ? p->C : p->k0_pad;
+  size_t n_max = p->C > p->k0_pad ? p->C : p->k0_pad;
+  if ((size_t)p->c_in_pad > n_max) n_max = p->c_in_pad;
+  if (!strided && p->cfg.filter_widths[0] > max_taps) max_taps = p->cfg.filter_widths[0];
   w.partial_bytes = (size_t)8 * max_taps * round_up(p->C, 128) * round_up((int)n_max, 64) * 4;
   w.partial = take(w.partial_bytes);
   w.total = off + 1024;
   return w;
 }
 
-// dW = dZ^T X for one conv layer.  dz: [planes][rows][dz_ld]; x: [planes][rows][x_ld].
-int run_wgrad(const vp3d_plan* p, const __nv_bfloat16* dz, int dz_ld, const __nv_bfloat16* x,
-              int x_ld, long long rows, int taps, int tap_col_step, int c_out, int c_in_cols,
-              int c_in, int taps_out, int merged, float* grad, float* partial, size_t partial_bytes,
+// dW = dZ^T X for one conv layer.  dz: [planes][samples][rows][dz_ld]; x: [planes][samples][x_rows][x_ld]
+// (flat layers: samples = 1).
+struct WgradCall {
+  const __nv_bfloat16* dz = nullptr;
+  int dz_ld = 0;
+  const __nv_bfloat16* x = nullptr;
+  int x_ld = 0;
+  long long rows = 0;     // dZ rows (per sample when per_sample)
+  int per_sample = 0;
+  int samples = 1;
+  long long x_rows = 0;   // X rows per sample (per_sample only)
+  int taps = 1;
+  int tap_col_step = 0;
+  int tap_row_step = 0;
+  int c_out = 0;
+  int c_in_cols = 0;      // columns of X spanned by one tap (merged: taps*c_in)
+  int c_in = 0;
+  int taps_out = 1;
+  int merged = 0;
+  float* grad = nullptr;
+};
+
+int run_wgrad(const vp3d_plan* p, const WgradCall& c, float* partial, size_t partial_bytes,
               cudaStream_t stream) {
-  const int block_n = pick_block_n(round_up(c_in_cols, 64));
+  const int block_n = pick_block_n(round_up(c.c_in_cols, 64));
   WgradArgs a;
   memset(&a, 0, sizeof(a));
-  a.per_sample = 0;
-  a.samples = 1;
-  a.rows = (int)rows;
-  a.kchunks = (int)((rows + 63) / 64);
-  a.taps = taps;
-  a.tap_row_step = 0;
-  a.tap_col_step = tap_col_step;
-  a.m_pad = round_up(c_out, 128);
-  a.n_pad = round_up(c_in_cols, block_n);
+  a.per_sample = c.per_sample;
+  a.samples = c.per_sample ? c.samples : 1;
+  a.rows = (int)c.rows;
+  a.kchunks = (int)((c.rows + 63) / 64);
+  a.taps = c.taps;
+  a.tap_row_step = c.tap_row_step;
+  a.tap_col_step = c.tap_col_step;
+  a.m_pad = round_up(c.c_out, 128);
+  a.n_pad = round_up(c.c_in_cols, block_n);
   a.m_tiles = a.m_pad / 128;
   a.n_tiles = a.n_pad / block_n;
   a.pairs = p->planes == 2 ? 3 : 1;
-  const int items = taps * a.m_tiles * a.n_tiles;
+  const int items = c.taps * a.m_tiles * a.n_tiles;
+  const long long total_kb = (long long)a.kchunks * a.samples;
   int splits = (2 * num_sms() + items - 1) / items;
   if (splits > 8) splits = 8;
-  if (splits > a.kchunks) splits = a.kchunks;
+  if (splits > total_kb) splits = (int)total_kb;
   if (splits < 1) splits = 1;
-  while ((size_t)splits * taps * a.m_pad * a.n_pad * 4 > partial_bytes && splits > 1) --splits;
-  if ((size_t)splits * taps * a.m_pad * a.n_pad * 4 > partial_bytes)
+  while ((size_t)splits * c.taps * a.m_pad * a.n_pad * 4 > partial_bytes && splits > 1) --splits;
+  if ((size_t)splits * c.taps * a.m_pad * a.n_pad * 4 > partial_bytes)
     return fail(VP3D_ERR_WORKSPACE, "wgrad partial buffer too small");
   a.splits = splits;
   a.partial = partial;
   CUtensorMap mdz, mx;
-  VP3D_TRY(make_map_4d(&mdz, dz, dz_ld, rows, dz_ld, 1, (uint64_t)rows * dz_ld, p->planes,
-                       (uint64_t)rows * dz_ld, 64));
-  VP3D_TRY(make_map_4d(&mx, x, x_ld, rows, x_ld, 1, (uint64_t)rows * x_ld, p->planes,
-                       (uint64_t)rows * x_ld, 64));
+  const uint64_t x_rows = c.per_sample ? (uint64_t)c.x_rows : (uint64_t)c.rows;
+  VP3D_TRY(make_map_4d(&mdz, c.dz, c.dz_ld, c.rows, c.dz_ld, a.samples, (uint64_t)c.rows * c.dz_ld,
+                       p->planes, (uint64_t)a.samples * c.rows * c.dz_ld, 64));
+  VP3D_TRY(make_map_4d(&mx, c.x, c.x_ld, x_rows, c.x_ld, a.samples, x_rows * c.x_ld, p->planes,
+                       (uint64_t)a.samples * x_rows * c.x_ld, 64));
   CUDA_TRY(launch_wgrad_gemm(mdz, mx, a, block_n, num_sms(), stream));
-  CUDA_TRY(launch_wgrad_reduce(partial, grad, splits, taps, a.m_pad, a.n_pad, c_out, c_in, taps_out,
-                               merged, stream));
+  CUDA_TRY(launch_wgrad_reduce(partial, c.grad, splits, c.taps, a.m_pad, a.n_pad, c.c_out, c.c_in,
+                               c.taps_out, c.merged, stream));
   return VP3D_OK;
 }
 
@@ -206,8 +231,9 @@ using namespace vp3d;
 VP3D_API size_t vp3d_train_workspace_bytes(const vp3d_plan* p, int N, int T) {
   if (!p || N < 1) return 0;
   int L[VP3D_MAX_WIDTHS];
-  if (!layer_rows(p, T, true, L)) return 0;
-  return train_layout(p, N, L).total;
+  const bool strided = p->cfg.variant == VP3D_VARIANT_STRIDED;
+  if (!layer_rows(p, T, strided, L)) return 0;
+  return train_layout(p, N, T, L).total;
 }
 
 VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, int T,
@@ -215,10 +241,7 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
                                 unsigned long long seed, void* ws, size_t ws_bytes, void* stream_) {
   if (!p || !x || !y || !w || !bn_momentum)
     return fail(VP3D_ERR_INVALID, "forward_train: null argument");
-  if (p->cfg.variant != VP3D_VARIANT_STRIDED)
-    return fail(VP3D_ERR_UNSUPPORTED,
-                "training kernels cover TemporalModelOptimized1f (strided) only; TemporalModel in "
-                "train() mode is not built yet");
+  const bool strided = p->cfg.variant == VP3D_VARIANT_STRIDED;
   if (N < 1) return fail(VP3D_ERR_INVALID, "forward_train: batch must be >= 1");
   if (dropout_p < 0.0f || dropout_p >= 1.0f)
     return fail(VP3D_ERR_INVALID, "forward_train: dropout p must be in [0, 1)");
@@ -228,14 +251,14 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   if (!t->packed_t) return fail(VP3D_ERR_STATE, "forward_train: transposed weights not packed");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int L[VP3D_MAX_WIDTHS];
-  if (!layer_rows(p, T, true, L))
+  if (!layer_rows(p, T, strided, L))
     return fail(VP3D_ERR_INVALID, "forward_train: sequence of %d frames is too short", T);
   const int* fw = p->cfg.filter_widths;
-  for (int i = 1; i <= p->nb; ++i)
+  for (int i = 1; strided && i <= p->nb; ++i)
     if (L[i - 1] != fw[i] * L[i])
       return fail(VP3D_ERR_UNSUPPORTED, "strided training needs layer lengths divisible by the "
                   "filter width (block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
-  const TrainLayout wl = train_layout(p, N, L);
+  const TrainLayout wl = train_layout(p, N, T, L);
   if (!ws || ws_bytes < wl.total)
     return fail(VP3D_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes, wl.total);
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
@@ -272,14 +295,22 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   };
   const RowMap no_map = {0, 0, 1, 0};
 
-  // ---- expand (model.py:188)
-  CUDA_TRY(launch_pack_input(x, bf(wl.a0), pl, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
-                             wl.rows[0] * p->k0_pad, stream));
-  ++launches;
+  // ---- expand (model.py:188 strided / :127 dilated)
   common(d);
-  d.a = bf(wl.a0); d.a_rows = (int)wl.rows[0]; d.a_ld = p->k0_pad;
-  d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
-  d.out_rows = (int)wl.rows[0];
+  if (strided) {
+    CUDA_TRY(launch_pack_input(x, bf(wl.a0), pl, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
+                               wl.rows[0] * p->k0_pad, stream));
+    d.a = bf(wl.a0); d.a_rows = (int)wl.rows[0]; d.a_ld = p->k0_pad;
+    d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
+    d.out_rows = (int)wl.rows[0];
+  } else {
+    CUDA_TRY(launch_pack_input(x, bf(wl.a0), pl, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
+                               (long long)N * T * p->c_in_pad, stream));
+    d.a = bf(wl.a0); d.samples = N; d.a_rows = T; d.a_ld = p->c_in_pad;
+    d.w = p->expand_dil.w; d.taps = fw[0]; d.k_per_tap = p->c_in_pad; d.n_pad = C;
+    d.per_sample_tiles = 1; d.tap_row_step = 1; d.out_rows = L[0];
+  }
+  ++launches;
   d.out = bf(wl.z[0]); d.out_plane_stride = wl.rows[0] * C; d.out_ld = C;
   d.stats = layer_vec(p, 0).stats;
   VP3D_TRY(run_conv(&d, stream));
@@ -291,9 +322,14 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
     const long long rows = wl.rows[i];
     const int l1 = 2 * i - 1, l2 = 2 * i;
     common(d);
-    d.a = bf(wl.x[i - 1]); d.a_rows = (int)rows; d.a_ld = fw[i] * C;
     d.w = p->conv[2 * (i - 1)].w; d.taps = p->taps[i]; d.k_per_tap = C; d.n_pad = C;
-    d.tap_col_step = C; d.out_rows = (int)rows;
+    if (strided) {
+      d.a = bf(wl.x[i - 1]); d.a_rows = (int)rows; d.a_ld = fw[i] * C;
+      d.tap_col_step = C; d.out_rows = (int)rows;
+    } else {
+      d.a = bf(wl.x[i - 1]); d.samples = N; d.a_rows = L[i - 1]; d.a_ld = C;
+      d.per_sample_tiles = 1; d.tap_row_step = p->dilation[i]; d.out_rows = L[i];
+    }
     d.out = bf(wl.z[l1]); d.out_plane_stride = rows * C; d.out_ld = C;
     d.stats = layer_vec(p, l1).stats;
     VP3D_TRY(run_conv(&d, stream));
@@ -308,7 +344,8 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
     d.stats = layer_vec(p, l2).stats;
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
-    const RowMap rm = {0, 0, fw[i], fw[i] / 2 + p->shift_str[i]};
+    const RowMap rm = strided ? RowMap{0, 0, fw[i], fw[i] / 2 + p->shift_str[i]}
+                              : RowMap{L[i], L[i - 1], 1, p->pad[i] + p->shift_dil[i]};
     VP3D_TRY(bn(l2, w->layers_bn[2 * (i - 1) + 1], rows, bf(wl.z[l2]), bf(wl.x[i]), bf(wl.x[i - 1]),
                 wl.rows[i - 1] * C, rm));
   }
@@ -350,7 +387,8 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   const int N = t->N, C = p->C, pl = p->planes;
   const int* L = t->L;
   const int* fw = p->cfg.filter_widths;
-  const TrainLayout wl = train_layout(p, N, L);
+  const bool strided = p->cfg.variant == VP3D_VARIANT_STRIDED;
+  const TrainLayout wl = train_layout(p, N, t->T, L);
   if (!ws || ws_bytes < wl.total) return fail(VP3D_ERR_WORKSPACE, "backward: workspace too small");
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
@@ -394,8 +432,12 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   CUDA_TRY(cudaMemsetAsync(g->shrink_bias, 0, p->c_out_raw * sizeof(float), stream));
   CUDA_TRY(launch_col_sum_f32(dy, rows_top, p->c_out_raw, g->shrink_bias, stream));
   launches += 2;
-  VP3D_TRY(run_wgrad(p, bf(wl.dyp), co128, bf(wl.x[p->nb]), C, rows_top, 1, 0, p->c_out_raw, C, C, 1,
-                     0, g->shrink_weight, partial, wl.partial_bytes, stream));
+  {
+    WgradCall c;
+    c.dz = bf(wl.dyp); c.dz_ld = co128; c.x = bf(wl.x[p->nb]); c.x_ld = C; c.rows = rows_top;
+    c.c_out = p->c_out_raw; c.c_in_cols = C; c.c_in = C; c.grad = g->shrink_weight;
+    VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
+  }
   launches += 2;
   __nv_bfloat16* gb[2] = {bf(wl.g0), bf(wl.g1)};
   int cur = 0;
@@ -415,8 +457,12 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     const int c1 = 2 * (i - 1), c2 = c1 + 1;
     // second conv (1x1): X_i = res + act(bn(conv2(H_i)))
     VP3D_TRY(bn_bwd(l2, rows, gb[cur], bf(wl.z[l2]), g->layers_bn[c2][0], g->layers_bn[c2][1]));
-    VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.h[i]), C, rows, 1, 0, C, C, C, 1, 0,
-                       g->layers_conv_weight[c2], partial, wl.partial_bytes, stream));
+    {
+      WgradCall c;
+      c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.h[i]); c.x_ld = C; c.rows = rows;
+      c.c_out = C; c.c_in_cols = C; c.c_in = C; c.grad = g->layers_conv_weight[c2];
+      VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
+    }
     launches += 2;
     common(d);
     d.a = bf(wl.dz); d.a_rows = (int)rows; d.a_ld = C;
@@ -427,18 +473,43 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     ++launches;
     // first conv (w taps, stride w): H_i = act(bn(conv1(X_{i-1})))
     VP3D_TRY(bn_bwd(l1, rows, gb[cur ^ 1], bf(wl.z[l1]), g->layers_bn[c1][0], g->layers_bn[c1][1]));
-    VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.x[i - 1]), fw[i] * C, rows, p->taps[i], C, C, C, C,
-                       p->taps[i], 0, g->layers_conv_weight[c1], partial, wl.partial_bytes, stream));
+    {
+      WgradCall c;
+      c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.x[i - 1]); c.taps = p->taps[i];
+      c.c_out = C; c.c_in_cols = C; c.c_in = C; c.taps_out = p->taps[i];
+      c.grad = g->layers_conv_weight[c1];
+      if (strided) {
+        c.x_ld = fw[i] * C; c.rows = rows; c.tap_col_step = C;
+      } else {
+        c.x_ld = C; c.per_sample = 1; c.samples = N; c.rows = L[i]; c.x_rows = L[i - 1];
+        c.tap_row_step = p->dilation[i];
+      }
+      VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
+    }
     launches += 2;
-    // G_{i-1}[rows, w*C] = dZ1 * W1^T  (+ G_i in the columns of the residual tap)
     common(d);
-    d.a = bf(wl.dz); d.a_rows = (int)rows; d.a_ld = C;
-    d.w = t->conv_t[c1]; d.taps = 1; d.k_per_tap = C; d.n_pad = p->taps[i] * C;
-    d.out_rows = (int)rows;
-    d.out = gb[cur ^ 1]; d.out_plane_stride = rows * fw[i] * C; d.out_ld = fw[i] * C;
+    d.w = t->conv_t[c1]; d.k_per_tap = C;
     d.res = gb[cur]; d.res_planes = pl; d.res_plane_stride = rows * C; d.res_ld = C;
-    d.res_rows_per_sample = 0; d.res_row_step = 1; d.res_row_off = 0;
-    d.res_col_begin = (fw[i] / 2 + p->shift_str[i]) * C; d.res_cols = C;
+    d.out = gb[cur ^ 1];
+    if (strided) {
+      // G_{i-1}[rows, w*C] = dZ1 * W1^T  (+ G_i in the columns of the residual tap)
+      d.a = bf(wl.dz); d.a_rows = (int)rows; d.a_ld = C;
+      d.taps = 1; d.n_pad = p->taps[i] * C;
+      d.out_rows = (int)rows;
+      d.out_plane_stride = rows * fw[i] * C; d.out_ld = fw[i] * C;
+      d.res_rows_per_sample = 0; d.res_row_step = 1; d.res_row_off = 0;
+      d.res_col_begin = (fw[i] / 2 + p->shift_str[i]) * C; d.res_cols = C;
+    } else {
+      // transposed convolution: G_{i-1}[n, t] = sum_k dZ1[n, t - k*d] * W1_k^T  (+ G_i[n, t - off]);
+      // rows outside [0, L_i) are zero-filled by the A / residual tensor maps
+      d.a = bf(wl.dz); d.samples = N; d.a_rows = L[i]; d.a_ld = C;
+      d.taps = p->taps[i]; d.n_pad = C; d.per_sample_tiles = 1;
+      d.tap_row_step = -p->dilation[i];
+      d.out_rows = L[i - 1];
+      d.out_plane_stride = wl.rows[i - 1] * C; d.out_ld = C;
+      d.res_rows_per_sample = L[i]; d.res_row_step = 1;
+      d.res_row_off = -(p->pad[i] + p->shift_dil[i]); d.res_check_rows = 1;
+    }
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     cur ^= 1;
@@ -447,9 +518,18 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
 
   // ---- expand backward (no data gradient: the 2-D input needs none, run.py:402-412)
   VP3D_TRY(bn_bwd(0, wl.rows[0], gb[cur], bf(wl.z[0]), g->expand_bn[0], g->expand_bn[1]));
-  VP3D_TRY(run_wgrad(p, bf(wl.dz), C, bf(wl.a0), p->k0_pad, wl.rows[0], 1, 0, C,
-                     fw[0] * p->c_in_raw, p->c_in_raw, fw[0], 1, g->expand_conv_weight, partial,
-                     wl.partial_bytes, stream));
+  {
+    WgradCall c;
+    c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.a0); c.c_out = C; c.c_in = p->c_in_raw;
+    c.taps_out = fw[0]; c.grad = g->expand_conv_weight;
+    if (strided) {
+      c.x_ld = p->k0_pad; c.rows = wl.rows[0]; c.c_in_cols = fw[0] * p->c_in_raw; c.merged = 1;
+    } else {
+      c.x_ld = p->c_in_pad; c.per_sample = 1; c.samples = N; c.rows = L[0]; c.x_rows = t->T;
+      c.taps = fw[0]; c.tap_row_step = 1; c.c_in_cols = p->c_in_raw;
+    }
+    VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
+  }
   launches += 2;
   if (stage_done) stage_done(p->nb + 1, user);  // expand_conv / expand_bn
   p->last_launches = launches;

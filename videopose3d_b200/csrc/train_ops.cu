@@ -118,6 +118,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
   float sc[8], sh[8];
   load_vec8(scale + c0, sc);
   load_vec8(shift + c0, sh);
+#pragma unroll 4
   for (long long r = r_begin + rl; r < r_end; r += 32) {
     float v[8];
     load8(z + r * c + c0, z_plane, planes, v);
@@ -180,6 +181,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
   load_vec8(shift + c0, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.0f;
+#pragma unroll 4
   for (long long r = r_begin + rl; r < r_end; r += 32) {
     float dy[8], zv[8];
     dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);
@@ -258,6 +260,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
       D[j] = -sc[j] * s1[j] * inv_n - B[j] * mu[j];
     }
   }
+#pragma unroll 4
   for (long long r = r_begin + rl; r < r_end; r += 32) {
     float dy[8], zv[8], o[8];
     dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);

@@ -298,10 +298,6 @@ class TemporalModelBase(nn.Module):
         return y
 
     def _forward_train(self, x):
-        if self._variant != _capi.VP3D_VARIANT_STRIDED:
-            raise NotImplementedError(
-                "training kernels cover TemporalModelOptimized1f (the model run.py trains with); "
-                "TemporalModel in train() mode is not built yet — there is no PyTorch fallback")
         params = self._learnable_tensors()
         return _TrainFunction.apply(self, x.contiguous(), *params)
 
