@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -683,7 +684,11 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host(vp3
   // Batch rows are independent in eval mode: split the batch into chunks so that the host->device
   // copy of chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream).  PCIe moves
   // 33.8 MB per 1024 x 243 batch, which is longer than the whole forward.
-  const int chunks = N >= 512 ? 4 : (N >= 128 ? 2 : 1);
+  int chunks = N >= 512 ? 2 : 1;
+  if (const char* env = getenv("VP3D_HOST_CHUNKS")) {  // measurement knob
+    const int c = atoi(env);
+    if (c >= 1 && c <= 16 && c <= N) chunks = c;
+  }
   if (chunks == 1) {
     CUDA_TRY(cudaMemcpyAsync(p->d_x, x_host, xb, cudaMemcpyHostToDevice, p->stream));
     VP3D_TRY(vp3d_forward_eval(p, p->d_x, p->d_y, N, T, p->d_ws, p->d_ws_bytes, p->stream));
