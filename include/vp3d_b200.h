@@ -118,6 +118,15 @@ int vp3d_forward_eval(vp3d_plan* plan, const float* x, float* y, int N, int T, v
  * for full PCIe bandwidth but pageable memory is accepted. */
 int vp3d_forward_eval_host(vp3d_plan* plan, const float* x_host, float* y_host, int N, int T);
 
+/* Pipelined form of vp3d_forward_eval_host for streams of batches (the evaluation loop of
+ * run.py:663-721 visits one batch after another): submit() enqueues copy-in -> forward -> copy-out
+ * for one batch on slot 0 or 1 and returns; wait() blocks until that slot's y_host is complete.
+ * Alternating the two slots overlaps the PCIe copy of batch i+1 with the kernels of batch i.
+ * x_host / y_host must stay valid (and should be pinned) until wait() returns. */
+int vp3d_forward_eval_host_submit(vp3d_plan* plan, const float* x_host, float* y_host, int N, int T,
+                                  int slot);
+int vp3d_forward_eval_host_wait(vp3d_plan* plan, int slot);
+
 /* ---- training (TemporalModelOptimized1f; run.py:318-420) ------------------------------------
  * Gradient buffers, one per learnable tensor of the state_dict (same shapes, fp32, device).  They
  * are OVERWRITTEN by vp3d_backward (autograd accumulates them into .grad on the Python side). */

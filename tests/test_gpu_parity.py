@@ -168,6 +168,27 @@ def test_forward_host_matches_device(cuda_device):
     assert _rel(y_h.numpy(), y_ref) <= 1e-3
 
 
+def test_pipelined_host_api_matches_device(cuda_device):
+    """Two-slot submit / wait: results of interleaved batches land in the right buffers."""
+    meta, sd, x, y_ref, _ = load_golden("tm_333_c64")
+    m = _build(meta, sd, cuda_device, "bf16x3")
+    xs = [x.pin_memory(), (x * 0.5).pin_memory(), (-x).pin_memory()]
+    with torch.no_grad():
+        expect = [m(t.to(cuda_device)).cpu() for t in xs]
+    outs = [torch.empty_like(expect[0]).pin_memory() for _ in xs]
+    m.forward_host_submit(xs[0], outs[0], 0)
+    m.forward_host_submit(xs[1], outs[1], 1)
+    with pytest.raises(RuntimeError):
+        m.forward_host_submit(xs[2], outs[2], 1)      # slot still in flight
+    m.forward_host_wait(0)
+    m.forward_host_submit(xs[2], outs[2], 0)
+    m.forward_host_wait(1)
+    m.forward_host_wait(0)
+    for o, e in zip(outs, expect):
+        assert torch.equal(o, e)
+    assert _rel(outs[0].numpy(), y_ref) <= 1e-3
+
+
 def test_errors(cuda_device):
     meta, sd, x, _, _ = load_golden("tm_333_c64")
     m = _build(meta, sd, cuda_device, "bf16")

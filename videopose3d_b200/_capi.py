@@ -122,6 +122,10 @@ SIGNATURES = {
                                          ctypes.c_size_t, ctypes.c_void_p]),
     "vp3d_forward_eval_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int, ctypes.c_int]),
+    "vp3d_forward_eval_host_submit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_int]),
+    "vp3d_forward_eval_host_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "vp3d_train_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "vp3d_forward_train": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.POINTER(Weights),

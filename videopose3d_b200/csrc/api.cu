@@ -354,6 +354,12 @@ extern "C" __attribute__((visibility("default"))) void vp3d_plan_destroy(vp3d_pl
   if (p->d_y) cudaFree(p->d_y);
   if (p->d_ws) cudaFree(p->d_ws);
   if (p->stream) cudaStreamDestroy(p->stream);
+  for (auto& s : p->slots) {
+    if (s.d_x) cudaFree(s.d_x);
+    if (s.d_y) cudaFree(s.d_y);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+  }
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   for (cudaEvent_t e : p->copy_events) cudaEventDestroy(e);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -722,6 +728,66 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host(vp3
   }
   CUDA_TRY(cudaMemcpyAsync(y_host, p->d_y, yb, cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return VP3D_OK;
+}
+
+// Pipelined host API: submit() enqueues H2D (copy stream) -> forward (compute stream) -> D2H for one
+// batch and returns immediately; wait() blocks until that batch's output is in y_host.  With two
+// slots the PCIe copy of batch i+1 overlaps the kernels of batch i, so the sustained rate is
+// max(copy, compute) instead of their sum.
+extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host_submit(
+    vp3d_plan* p, const float* x_host, float* y_host, int N, int T, int slot) {
+  if (!p || !x_host || !y_host) return fail(VP3D_ERR_INVALID, "host_submit: null argument");
+  if (slot < 0 || slot > 1) return fail(VP3D_ERR_INVALID, "host_submit: slot must be 0 or 1");
+  const int t_out = vp3d_output_frames(p, T);
+  if (t_out < 1 || N < 1) return fail(VP3D_ERR_INVALID, "host_submit: bad shape");
+  vp3d_plan::HostSlot& s = p->slots[slot];
+  if (s.busy) return fail(VP3D_ERR_STATE, "host_submit: slot %d still in flight (call wait first)", slot);
+  if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (!p->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  if (!s.copied) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  const size_t xb = (size_t)N * T * p->c_in_raw * sizeof(float);
+  const size_t yb = (size_t)N * t_out * p->c_out_raw * sizeof(float);
+  const size_t wb = vp3d_workspace_bytes(p, N, T);
+  if (xb > s.x_bytes) {
+    if (s.d_x) cudaFree(s.d_x);
+    s.d_x = nullptr; s.x_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s.d_x, xb));
+    s.x_bytes = xb;
+  }
+  if (yb > s.y_bytes) {
+    if (s.d_y) cudaFree(s.d_y);
+    s.d_y = nullptr; s.y_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s.d_y, yb));
+    s.y_bytes = yb;
+  }
+  if (wb > p->d_ws_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(p->stream));  // the other slot may be using the old workspace
+    if (p->d_ws) cudaFree(p->d_ws);
+    p->d_ws = nullptr; p->d_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&p->d_ws, wb));
+    p->d_ws_bytes = wb;
+  }
+  CUDA_TRY(cudaMemcpyAsync(s.d_x, x_host, xb, cudaMemcpyHostToDevice, p->copy_stream));
+  CUDA_TRY(cudaEventRecord(s.copied, p->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(p->stream, s.copied, 0));
+  VP3D_TRY(vp3d_forward_eval(p, s.d_x, s.d_y, N, T, p->d_ws, p->d_ws_bytes, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(y_host, s.d_y, yb, cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaEventRecord(s.done, p->stream));
+  s.busy = true;
+  return VP3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval_host_wait(vp3d_plan* p,
+                                                                                 int slot) {
+  if (!p || slot < 0 || slot > 1) return fail(VP3D_ERR_INVALID, "host_wait: bad argument");
+  vp3d_plan::HostSlot& s = p->slots[slot];
+  if (!s.busy) return fail(VP3D_ERR_STATE, "host_wait: slot %d has nothing in flight", slot);
+  CUDA_TRY(cudaEventSynchronize(s.done));
+  s.busy = false;
   return VP3D_OK;
 }
 

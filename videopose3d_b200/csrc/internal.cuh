@@ -77,6 +77,15 @@ struct vp3d_plan {
   cudaStream_t copy_stream = nullptr;     // host API: H2D chunks overlap the compute stream
   std::vector<cudaEvent_t> copy_events;
   int last_launches = 0;
+  // pipelined host API (vp3d_forward_eval_host_submit / _wait): two independent staging slots
+  struct HostSlot {
+    float* d_x = nullptr;
+    float* d_y = nullptr;
+    size_t x_bytes = 0, y_bytes = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false;
+  };
+  HostSlot slots[2];
   // measurement hook: event pairs around one chosen launch of each forward
   int prof_launch = -1;
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs

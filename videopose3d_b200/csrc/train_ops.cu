@@ -95,7 +95,12 @@ __device__ __forceinline__ long long map_row(const RowMap& m, long long r) {
 // 64 channels per block) x 32 row lanes; a block walks kRowsPerBlock rows.  Per-channel vectors are
 // loaded once into registers and reused for every row the thread touches; a warp's access is 4 rows
 // x 128 contiguous bytes.
-constexpr int kRowsPerBlock = 256;
+// G = column groups per block (power of two dividing c/8, <= 256), lanes = 256 / G row lanes.  For
+// C = 1024 a block spans whole rows (G = 128): every warp reads 512 contiguous bytes.
+struct RowTiling {
+  int G;               // column groups (of 8 channels) handled by one block
+  int rows_per_block;  // rows walked by one block
+};
 
 __device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -107,11 +112,12 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
                 __nv_bfloat16* __restrict__ x, long long x_plane, int planes, long long rows, int c,
                 const float* __restrict__ scale, const float* __restrict__ shift, DropoutCfg drop,
-                const __nv_bfloat16* __restrict__ res, long long res_plane, RowMap map) {
-  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
-  const int c0 = blockIdx.x * 64 + cg * 8;
-  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
-  const long long r_end = min(rows, r_begin + kRowsPerBlock);
+                const __nv_bfloat16* __restrict__ res, long long res_plane, RowMap map,
+                RowTiling tl) {
+  const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
+  const int c0 = (blockIdx.x * tl.G + cg) * 8;
+  const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
+  const long long r_end = min(rows, r_begin + tl.rows_per_block);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
@@ -119,7 +125,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
   load_vec8(scale + c0, sc);
   load_vec8(shift + c0, sh);
 #pragma unroll 4
-  for (long long r = r_begin + rl; r < r_end; r += 32) {
+  for (long long r = r_begin + rl; r < r_end; r += lanes) {
     float v[8];
     load8(z + r * c + c0, z_plane, planes, v);
 #pragma unroll
@@ -165,13 +171,13 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
                      const __nv_bfloat16* __restrict__ z, long long z_plane, int planes,
                      long long rows, int c, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, DropoutCfg drop, float* __restrict__ sums) {
-  __shared__ float sm[2][8][64];
-  const int cg = threadIdx.x & 7;
-  const int rl = threadIdx.x >> 3;
-  const int c0 = blockIdx.x * 64 + cg * 8;
-  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
-  const long long r_end = min(rows, r_begin + kRowsPerBlock);
+                     const float* __restrict__ invstd, DropoutCfg drop, float* __restrict__ sums,
+                     RowTiling tl) {
+  __shared__ float sm[2][2048];
+  const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
+  const int c0 = (blockIdx.x * tl.G + cg) * 8;
+  const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
+  const long long r_end = min(rows, r_begin + tl.rows_per_block);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
@@ -182,7 +188,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.0f;
 #pragma unroll 4
-  for (long long r = r_begin + rl; r < r_end; r += 32) {
+  for (long long r = r_begin + rl; r < r_end; r += lanes) {
     float dy[8], zv[8];
     dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);
 #pragma unroll
@@ -193,30 +199,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
   }
   float is[8];
   load_vec8(invstd + c0, is);
-  // the 4 row lanes sharing a warp: lanes differ in bits 3,4
+  const int width = tl.G * 8;  // channels covered by this block
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    s2[j] *= is[j];
-    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sm[0][warp][lane * 8 + j] = s1[j];
-      sm[1][warp][lane * 8 + j] = s2[j];
-    }
+    sm[0][rl * width + cg * 8 + j] = s1[j];
+    sm[1][rl * width + cg * 8 + j] = s2[j] * is[j];
   }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+  for (int i = threadIdx.x; i < 2 * width; i += 256) {
+    const int which = i / width, ch = i - which * width;
     float t = 0.0f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[which][w][col];
-    atomicAdd(sums + which * c + blockIdx.x * 64 + col, t);
+    for (int l = 0; l < lanes; ++l) t += sm[which][l * width + ch];
+    atomicAdd(sums + which * c + blockIdx.x * width + ch, t);
   }
 }
 
@@ -229,11 +223,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
                     int c, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     DropoutCfg drop, const float* __restrict__ sums, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta) {
-  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
-  const int c0 = blockIdx.x * 64 + cg * 8;
-  const long long r_begin = (long long)blockIdx.y * kRowsPerBlock;
-  const long long r_end = min(rows, r_begin + kRowsPerBlock);
+                    float* __restrict__ dbeta, RowTiling tl) {
+  const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
+  const int c0 = (blockIdx.x * tl.G + cg) * 8;
+  const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
+  const long long r_end = min(rows, r_begin + tl.rows_per_block);
   const bool do_drop = drop.p > 0.0f;
   const uint32_t thresh = (uint32_t)(drop.p * 65536.0f);
   const float inv_keep = do_drop ? 1.0f / (1.0f - drop.p) : 1.0f;
@@ -261,7 +255,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
     }
   }
 #pragma unroll 4
-  for (long long r = r_begin + rl; r < r_end; r += 32) {
+  for (long long r = r_begin + rl; r < r_end; r += lanes) {
     float dy[8], zv[8], o[8];
     dy8(g, g_plane, z, z_plane, planes, r, c, c0, sc, sh, drop, do_drop, thresh, inv_keep, dy, zv);
 #pragma unroll
@@ -314,11 +308,21 @@ pack_conv_weight_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict
   }
 }
 
-int grid_for(long long total, int threads) {
-  long long b = (total + threads - 1) / threads;
-  if (b > 148 * 16) b = 148 * 16;
-  if (b < 1) b = 1;
-  return (int)b;
+RowTiling row_tiling(long long rows, int c, dim3& grid) {
+  RowTiling tl;
+  const int groups = c / 8;
+  tl.G = 8;
+  while (tl.G * 2 <= 256 && groups % (tl.G * 2) == 0) tl.G *= 2;
+  const int lanes = 256 / tl.G;
+  const int col_blocks = groups / tl.G;
+  // enough blocks to fill the chip twice, at least 4 rows per thread, at most 256 rows per block
+  long long rpb = rows * col_blocks / (2 * 148);
+  if (rpb > 256) rpb = 256;
+  if (rpb < 4LL * lanes) rpb = 4LL * lanes;
+  rpb = (rpb + lanes - 1) / lanes * lanes;
+  tl.rows_per_block = (int)rpb;
+  grid = dim3(col_blocks, (unsigned)((rows + rpb - 1) / rpb));
+  return tl;
 }
 
 }  // namespace
@@ -338,9 +342,10 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bflo
                             const float* shift, DropoutCfg drop, const __nv_bfloat16* res,
                             long long res_plane, RowMap map, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  dim3 grid;
+  const RowTiling tl = row_tiling(rows, c, grid);
   bn_apply_kernel<<<grid, 256, 0, stream>>>(z, z_plane, x, x_plane, planes, rows, c, scale, shift,
-                                            drop, res, res_plane, map);
+                                            drop, res, res_plane, map, tl);
   return cudaGetLastError();
 }
 
@@ -350,9 +355,10 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, cons
                                  const float* invstd, DropoutCfg drop, float* sums,
                                  cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  dim3 grid;
+  const RowTiling tl = row_tiling(rows, c, grid);
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
-                                                 shift, mean, invstd, drop, sums);
+                                                 shift, mean, invstd, drop, sums, tl);
   return cudaGetLastError();
 }
 
@@ -362,10 +368,11 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
                                 const float* mean, const float* invstd, DropoutCfg drop,
                                 const float* sums, float* dgamma, float* dbeta, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  dim3 grid(c / 64, (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+  dim3 grid;
+  const RowTiling tl = row_tiling(rows, c, grid);
   bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, dz, dz_plane, planes, rows,
                                                 c, scale, shift, mean, invstd, drop, sums, dgamma,
-                                                dbeta);
+                                                dbeta, tl);
   return cudaGetLastError();
 }
 

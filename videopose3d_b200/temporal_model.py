@@ -356,6 +356,36 @@ class TemporalModelBase(nn.Module):
                         "vp3d_forward_eval_host")
         return out
 
+    def forward_host_submit(self, x_host, out, slot):
+        """Pipelined form of forward_host: enqueue copy-in -> kernels -> copy-out for one batch on
+        `slot` (0 or 1) and return immediately; `forward_host_wait(slot)` completes it.  Alternating
+        the slots overlaps the PCIe copy of the next batch with the kernels of the current one.
+        `x_host` and `out` must be pinned CPU float32 tensors that stay alive until the wait."""
+        lib = _capi.load()
+        if self.training:
+            raise RuntimeError("forward_host_submit is an eval-mode call")
+        if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise ValueError("forward_host_submit expects a contiguous float32 CPU tensor")
+        assert x_host.dim() == 4 and x_host.shape[-2] == self.num_joints_in \
+            and x_host.shape[-1] == self.in_features
+        device = self.expand_conv.weight.device
+        N, T = int(x_host.shape[0]), int(x_host.shape[1])
+        with torch.cuda.device(device):
+            plan = self._get_plan(device)
+            stream = torch.cuda.current_stream(device)
+            before = self._packed.get((self._plan_key, False))
+            self._sync_weights(plan, stream.cuda_stream)
+            if self._packed.get((self._plan_key, False)) is not before:
+                stream.synchronize()  # freshly packed weights are read by the plan's own stream
+            _capi.check(lib.vp3d_forward_eval_host_submit(plan, x_host.data_ptr(), out.data_ptr(), N,
+                                                          T, int(slot)),
+                        "vp3d_forward_eval_host_submit")
+        return out
+
+    def forward_host_wait(self, slot):
+        _capi.check(_capi.load().vp3d_forward_eval_host_wait(self._plan, int(slot)),
+                    "vp3d_forward_eval_host_wait")
+
     def last_launch_count(self):
         return 0 if self._plan is None else _capi.load().vp3d_last_launch_count(self._plan)
 
