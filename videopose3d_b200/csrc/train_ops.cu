@@ -315,8 +315,9 @@ RowTiling row_tiling(long long rows, int c, dim3& grid) {
   while (tl.G * 2 <= 256 && groups % (tl.G * 2) == 0) tl.G *= 2;
   const int lanes = 256 / tl.G;
   const int col_blocks = groups / tl.G;
-  // enough blocks to fill the chip twice, at least 4 rows per thread, at most 256 rows per block
-  long long rpb = rows * col_blocks / (2 * 148);
+  // ~16 resident blocks per SM (the loads are latency-bound otherwise), at least 4 rows per thread,
+  // at most 256 rows per block
+  long long rpb = rows * col_blocks / (16 * 148);
   if (rpb > 256) rpb = 256;
   if (rpb < 4LL * lanes) rpb = 4LL * lanes;
   rpb = (rpb + lanes - 1) / lanes * lanes;
