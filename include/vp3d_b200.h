@@ -222,6 +222,19 @@ typedef struct {
   int out_f32_ld;
   int n_valid;
   float* stats;         /* [2][n_pad] sum / sum-of-squares accumulators or NULL */
+  /* fused BatchNorm-backward reductions (training data-gradient GEMMs, single-plane bf16 only):
+   * bnb_z = pre-BN output Z of the layer whose activation gradient this GEMM produces, same
+   * [rows][out_ld] view as `out`; accumulates sum(dY) and invstd*sum(dY*(Z-mean)) into bnb_sums. */
+  const void* bnb_z;    /* NULL = off */
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
+  float* bnb_sums;      /* [2][bnb_c] */
+  int bnb_c;            /* channels of that layer (column index modulo bnb_c) */
+  float bnb_p;          /* its dropout probability */
+  unsigned long long bnb_seed;
+  int bnb_layer;
 } vp3d_conv_desc;
 
 int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream);

@@ -52,20 +52,30 @@ def main():
 
     check = None
     if args.check and world > 1:
-        torch.manual_seed(7)  # same dropout seed draw on every rank is fine; data differs
-        object.__setattr__(m, "_grad_reducer", None)
-        opt.zero_grad()
-        torch.mean(torch.norm(m(x) - tgt, dim=-1)).backward()
-        ref = [p.grad.clone() for p in m.parameters()]
-        for t in ref:
-            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        # The BatchNorm batch sums use fp32 atomics, so two runs of the *same* step differ by ReLU
+        # mask flips; the noise floor (two plain runs) is reported next to the staged-path check.
+        def plain_avg():
+            torch.manual_seed(7)  # same dropout seed draw on every rank is fine; data differs
+            object.__setattr__(m, "_grad_reducer", None)
+            opt.zero_grad()
+            torch.mean(torch.norm(m(x) - tgt, dim=-1)).backward()
+            out = [p.grad.clone() for p in m.parameters()]
+            for t in out:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG)
+            return out
+
+        def rel_l2(a, b):
+            return max(float((p - r).norm() / r.norm().clamp_min(1e-20)) for p, r in zip(a, b))
+
+        ref, ref2 = plain_avg(), plain_avg()
         object.__setattr__(m, "_grad_reducer", red)
         torch.manual_seed(7)
         opt.zero_grad()
         torch.mean(torch.norm(m(x) - tgt, dim=-1)).backward()
         torch.cuda.synchronize()
-        check = max(float((p.grad - r).abs().max() / r.abs().max().clamp_min(1e-20))
-                    for p, r in zip(m.parameters(), ref))
+        staged = [p.grad for p in m.parameters()]
+        check = {"staged_vs_plain_rel_l2": rel_l2(staged, ref),
+                 "plain_vs_plain_rel_l2_noise_floor": rel_l2(ref2, ref)}
 
     def step():
         opt.zero_grad()

@@ -102,6 +102,16 @@ class ConvDesc(ctypes.Structure):
         ("out_f32_ld", ctypes.c_int),
         ("n_valid", ctypes.c_int),
         ("stats", ctypes.c_void_p),
+        ("bnb_z", ctypes.c_void_p),
+        ("bnb_scale", ctypes.c_void_p),
+        ("bnb_shift", ctypes.c_void_p),
+        ("bnb_mean", ctypes.c_void_p),
+        ("bnb_invstd", ctypes.c_void_p),
+        ("bnb_sums", ctypes.c_void_p),
+        ("bnb_c", ctypes.c_int),
+        ("bnb_p", ctypes.c_float),
+        ("bnb_seed", ctypes.c_ulonglong),
+        ("bnb_layer", ctypes.c_int),
     ]
 
 

@@ -238,7 +238,27 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
       g.res_tma_row_off = (int)row_off;
     }
   }
-  CUDA_TRY(launch_conv_gemm(ma, mw, mo, mr, g, block_n, num_sms(), stream));
+  // fused BatchNorm-backward reductions: Z rides the auxiliary TMA path with the output's geometry
+  CUtensorMap mz = mo;
+  g.bnb = 0;
+  if (d->bnb_z) {
+    if (!d->out || g.out_planes != 1 || (d->res && !g.res_tma) || d->bnb_c <= 0 || d->bnb_c % 64)
+      return fail(VP3D_ERR_INVALID, "conv_gemm: fused BN-backward needs a single-plane bf16 output, "
+                  "a TMA-loadable residual (if any) and bnb_c % 64 == 0");
+    const uint64_t o_rows = d->out_rows, o_ld = d->out_ld;
+    const uint64_t o_samples = d->per_sample_tiles ? d->samples : 1;
+    VP3D_TRY(make_map_4d(&mz, d->bnb_z, o_ld, o_rows, o_ld, o_samples, o_rows * o_ld, 1,
+                         o_samples * o_rows * o_ld, kBlockM));
+    g.bnb = 1;
+    g.bnb_c = d->bnb_c;
+    g.bnb_scale = d->bnb_scale; g.bnb_shift = d->bnb_shift; g.bnb_mean = d->bnb_mean;
+    g.bnb_invstd = d->bnb_invstd; g.bnb_sums = d->bnb_sums;
+    g.bnb_p = d->bnb_p;
+    g.bnb_seed_lo = (unsigned)(d->bnb_seed & 0xFFFFFFFFu);
+    g.bnb_seed_hi = (unsigned)(d->bnb_seed >> 32);
+    g.bnb_layer = (unsigned)d->bnb_layer;
+  }
+  CUDA_TRY(launch_conv_gemm(ma, mw, mo, mr, mz, g, block_n, num_sms(), stream));
   return VP3D_OK;
 }
 

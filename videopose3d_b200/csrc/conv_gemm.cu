@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out,
-                 const __grid_constant__ CUtensorMap tmap_res, const ConvGemmArgs p) {
+                 const __grid_constant__ CUtensorMap tmap_res,
+                 const __grid_constant__ CUtensorMap tmap_z, const ConvGemmArgs p) {
   using Cfg = GemmCfg<BLOCK_N, RES>;
   constexpr int kStages = Cfg::kStages;
 
@@ -110,14 +111,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int m_tiles = p.dilated ? p.samples * p.tiles_per_sample : p.tiles_per_sample;
   const int total_tiles = m_tiles * p.n_tiles;
   const int k_iters = p.pairs * p.taps * p.kblocks_per_tap;
-  // residual stages: one plane -> three tiles in flight; two planes -> one (hi, lo) pair
-  const int res_stages = (p.res_planes == 2) ? 1 : 3;
+  // auxiliary tiles per 64-column store block: the residual plane(s) and, for the fused
+  // BatchNorm-backward reductions, the Z tile.  Three 16 KiB slots -> 3 / tiles stages in flight.
+  const bool has_res = (p.flags & kEpiResidual) != 0;
+  const int aux_tiles = (has_res ? p.res_planes : 0) + (p.bnb ? 1 : 0);
+  const int res_stages = aux_tiles > 0 ? 3 / aux_tiles : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_out);
     if (RES) tma_prefetch_desc(&tmap_res);
+    if (RES && p.bnb) tma_prefetch_desc(&tmap_z);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -200,20 +205,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ------------------------------------------------------------ residual producer
     if (RES && lane == 0) {
       uint32_t rs = 0, rphase = 0;
-      const uint32_t bytes = p.res_planes * Cfg::kTileBytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_blk, sample, row0;
         tile_coords(p, tile, n_blk, sample, row0);
         for (int sb = 0; sb < BLOCK_N / 64; ++sb) {
           const int col = n_blk * BLOCK_N + sb * 64;
-          if (col < p.res_col_begin || col >= p.res_col_begin + p.res_cols) continue;
+          const bool res_here = has_res && col >= p.res_col_begin && col < p.res_col_begin + p.res_cols;
+          if (!res_here && !p.bnb) continue;
+          const int n_res = res_here ? p.res_planes : 0;
           mbar_wait(rempty_bar + rs * 8, rphase ^ 1);
-          mbar_expect_tx(rfull_bar + rs * 8, bytes);
-          for (int pl = 0; pl < p.res_planes; ++pl)
-            tma_load_4d(&tmap_res, rfull_bar + rs * 8,
-                        smem_res + (rs * p.res_planes + pl) * Cfg::kTileBytes,
+          mbar_expect_tx(rfull_bar + rs * 8, (n_res + (p.bnb ? 1 : 0)) * Cfg::kTileBytes);
+          const uint32_t slot0 = smem_res + rs * aux_tiles * Cfg::kTileBytes;
+          for (int pl = 0; pl < n_res; ++pl)
+            tma_load_4d(&tmap_res, rfull_bar + rs * 8, slot0 + pl * Cfg::kTileBytes,
                         col - p.res_col_begin + p.res_tma_col_off, row0 + p.res_tma_row_off, sample,
                         pl);
+          if (p.bnb)  // the Z tile always sits in the last slot of the stage
+            tma_load_4d(&tmap_z, rfull_bar + rs * 8, slot0 + (aux_tiles - 1) * Cfg::kTileBytes, col,
+                        row0, sample, 0);
           if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
         }
       }
@@ -297,18 +306,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
+        const bool aux_here = RES && (res_here || p.bnb);
         if (RES) {
+          if (aux_here && half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
           if (res_here) {
-            if (half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // residual tile(s) have landed
             for (int pl = 0; pl < p.res_planes; ++pl) {
-              const uint32_t src = smem_res + (rs * p.res_planes + pl) * Cfg::kTileBytes + stage_row;
+              const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
-            }
-            if (half == 1) {
-              mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the residual stage
-              if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
             }
           }
         } else if (res_here && res_ok) {
@@ -364,6 +370,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             ++store_seq;
           }
         }
+        if (RES && p.bnb) {
+          // dY = G(as stored) * dropmask/(1-p) * [Z*scale+shift > 0]; sums over this warp's 32 rows
+          float zf[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) zf[j] = 0.0f;
+          const uint32_t zsrc = smem_res + (rs * aux_tiles + aux_tiles - 1) * Cfg::kTileBytes + stage_row;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            add_bf16x8(zf + q * 8, ld_shared_v4(zsrc + (((half * 4 + q) ^ sw) << 4)));
+          const int ch0 = c0 % p.bnb_c;
+          const bool drop = p.bnb_p > 0.0f;
+          const uint32_t thresh = (uint32_t)(p.bnb_p * 65536.0f);
+          const float inv_keep = drop ? 1.0f / (1.0f - p.bnb_p) : 1.0f;
+          const unsigned long long elem0 = (unsigned long long)out_row * p.out_ld + c0;
+          const uint32_t key = p.bnb_seed_lo ^ (p.bnb_seed_hi * 0x7F4A7C15u) ^
+                               (p.bnb_layer * 0x632BE5ABu) ^
+                               ((uint32_t)((elem0 >> 1) >> 32) * 0x85EBCA77u);
+          const uint32_t pbase = (uint32_t)(elem0 >> 1);
+          float s[32], q2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float m0 = 1.0f, m1 = 1.0f;
+            if (drop) {
+              uint32_t h = (pbase + (j >> 1)) * 0x9E3779B1u + key;
+              h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+              m0 = ((h & 0xFFFFu) >= thresh) ? inv_keep : 0.0f;
+              m1 = ((h >> 16) >= thresh) ? inv_keep : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int jj = j + e;
+              // gradient exactly as the next pass will read it back (bf16-rounded)
+              const float g = __bfloat162float(__float2bfloat16_rn(v[jj]));
+              const float y = fmaf(zf[jj], __ldg(p.bnb_scale + ch0 + jj), __ldg(p.bnb_shift + ch0 + jj));
+              float dy = (valid && y > 0.0f) ? g : 0.0f;
+              dy *= e ? m1 : m0;
+              s[jj] = dy;
+              q2[jj] = dy * (zf[jj] - __ldg(p.bnb_mean + ch0 + jj));
+            }
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = lane & off;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = upper ? s[i] : s[i + off];
+              const float keep_s = upper ? s[i + off] : s[i];
+              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              const float send_q = upper ? q2[i] : q2[i + off];
+              const float keep_q = upper ? q2[i + off] : q2[i];
+              q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          atomicAdd(p.bnb_sums + ch0 + lane, s[0]);
+          atomicAdd(p.bnb_sums + p.bnb_c + ch0 + lane, q2[0] * __ldg(p.bnb_invstd + ch0 + lane));
+        }
+        if (RES && aux_here && half == 1) {
+          mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the auxiliary stage
+          if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
+        }
         if (do_stats) {
           // Per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce,
           // 31 shuffles per statistic; afterwards lane j owns channel c0 + j.
@@ -411,7 +477,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 template <int BLOCK_N, bool RES>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                               const ConvGemmArgs& args, int num_sms, cudaStream_t stream) {
+                               const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
+                               cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, RES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -426,25 +493,25 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   if (total <= 0) return cudaSuccess;
   const int grid = total < num_sms ? total : num_sms;
   conv_gemm_kernel<BLOCK_N, RES>
-      <<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, args);
+      <<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const ConvGemmArgs& args, int block_n, int num_sms,
-                             cudaStream_t stream) {
-  const bool res = args.res_tma != 0;
+                             const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
+                             int num_sms, cudaStream_t stream) {
+  const bool res = args.res_tma != 0 || args.bnb != 0;
   switch (block_n) {
     case 256:
-      return res ? launch_impl<256, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
-                 : launch_impl<256, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+      return res ? launch_impl<256, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<256, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 128:
-      return res ? launch_impl<128, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
-                 : launch_impl<128, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+      return res ? launch_impl<128, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<128, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 64:
-      return res ? launch_impl<64, true>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream)
-                 : launch_impl<64, false>(tmap_a, tmap_w, tmap_out, tmap_res, args, num_sms, stream);
+      return res ? launch_impl<64, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<64, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     default:
       return cudaErrorInvalidValue;
   }

@@ -67,6 +67,21 @@ struct ConvGemmArgs {
   int res_tma;                  // 1: residual tiles are TMA-loaded by warp 3 through tmap_res (RES variant)
   int res_tma_col_off;          //   column offset inside the residual map's row view
   int res_tma_row_off;          //   row offset (added to the tile's first row)
+  // ---- fused BatchNorm-backward reductions (training data-gradient GEMMs, single-plane bf16):
+  // the GEMM output G is the gradient w.r.t. the activation of the layer below, whose pre-BN
+  // output Z has the same [rows][ld] view.  With the Z tile TMA-loaded next to the residual tile the
+  // epilogue forms dY = G * dropmask/(1-p) * [Z*scale+shift > 0] and accumulates sum(dY) and
+  // invstd * sum(dY * (Z - mean)) per channel (channel = column % bnb_c), replacing a separate
+  // pass over G and Z.
+  int bnb;                      // 1: enabled (requires the RES kernel variant and tmap_z)
+  int bnb_c;
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
+  float* bnb_sums;              // [2][bnb_c]
+  float bnb_p;                  // dropout probability of that layer (0 = none)
+  unsigned bnb_seed_lo, bnb_seed_hi, bnb_layer;
   __nv_bfloat16* out;          // bf16 output plane 0, [samples*out_rows, out_ld]
   long long out_plane_stride;
   int out_planes;              // 1 or 2
@@ -82,9 +97,10 @@ struct ConvGemmArgs {
 // pass any valid map — when the launch writes fp32).
 // tmap_res: 4-D (channel, row, sample, plane) over the residual's row view, box (64, 128, 1, 1); used
 // only when args.res_tma is set.
+// tmap_z: same geometry as tmap_out over the Z tensor of the layer below; used only when args.bnb.
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const ConvGemmArgs& args, int block_n, int num_sms,
-                             cudaStream_t stream);
+                             const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
+                             int num_sms, cudaStream_t stream);
 
 }  // namespace vp3d

@@ -412,17 +412,32 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     q.samples = 1;
     q.per_sample_tiles = 0;
   };
+  // In single-plane bf16 mode the per-channel reductions of the BatchNorm backward are fused into
+  // the epilogue of the GEMM that produces the incoming gradient (fuse_bnb); otherwise a separate
+  // pass over (G, Z) computes them.
+  const bool fuse = (pl == 1);
+  auto fuse_bnb = [&](vp3d_conv_desc& q, int layer) {
+    if (!fuse) return;
+    const LayerVec v = layer_vec(p, layer);
+    q.bnb_z = bf(wl.z[layer]);
+    q.bnb_scale = v.scale; q.bnb_shift = v.shift; q.bnb_mean = v.mean; q.bnb_invstd = v.invstd;
+    q.bnb_sums = v.sums; q.bnb_c = C; q.bnb_p = t->dropout_p; q.bnb_seed = t->seed;
+    q.bnb_layer = layer;
+  };
   // BN + ReLU + dropout backward of `layer`: (gin, z) -> dz (+ dgamma, dbeta)
   auto bn_bwd = [&](int layer, long long rows, const __nv_bfloat16* gin, const __nv_bfloat16* z,
                     float* dgamma, float* dbeta) -> int {
     const LayerVec v = layer_vec(p, layer);
     const DropoutCfg dc = drop_cfg(t, layer);
-    CUDA_TRY(launch_bn_bwd_reduce(gin, rows * C, z, rows * C, pl, rows, C, v.scale, v.shift, v.mean,
-                                  v.invstd, dc, v.sums, stream));
+    if (!fuse) {
+      CUDA_TRY(launch_bn_bwd_reduce(gin, rows * C, z, rows * C, pl, rows, C, v.scale, v.shift,
+                                    v.mean, v.invstd, dc, v.sums, stream));
+      ++launches;
+    }
     CUDA_TRY(launch_bn_bwd_apply(gin, rows * C, z, rows * C, bf(wl.dz), rows * C, pl, rows, C,
                                  v.scale, v.shift, v.mean, v.invstd, dc, v.sums, dgamma, dbeta,
                                  stream));
-    launches += 2;
+    ++launches;
     return VP3D_OK;
   };
 
@@ -446,6 +461,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   d.w = t->shrink_t; d.taps = 1; d.k_per_tap = co128; d.n_pad = C;
   d.out_rows = (int)rows_top;
   d.out = gb[cur]; d.out_plane_stride = rows_top * C; d.out_ld = C;
+  fuse_bnb(d, 2 * p->nb);  // G_nb feeds the BN backward of the top block's second conv (or expand)
   VP3D_TRY(run_conv(&d, stream));
   ++launches;
   if (stage_done) stage_done(0, user);  // shrink.weight / shrink.bias gradients are enqueued
@@ -469,6 +485,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     d.w = t->conv_t[c2]; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
     d.out_rows = (int)rows;
     d.out = gb[cur ^ 1]; d.out_plane_stride = rows * C; d.out_ld = C;
+    fuse_bnb(d, l1);
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     // first conv (w taps, stride w): H_i = act(bn(conv1(X_{i-1})))
@@ -510,6 +527,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
       d.res_rows_per_sample = L[i]; d.res_row_step = 1;
       d.res_row_off = -(p->pad[i] + p->shift_dil[i]); d.res_check_rows = 1;
     }
+    fuse_bnb(d, 2 * (i - 1));  // G_{i-1}: BN backward of block i-1's second conv (expand for i = 1)
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     cur ^= 1;
