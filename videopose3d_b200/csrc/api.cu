@@ -417,16 +417,20 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
                                      p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream));
     CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
                                      p->c_in_raw, w0, p->C, p->k0_pad, 1, stream));
+    // with VP3D_PACK_CONV_T the transposed-pack kernels below also write these forward packs
+    const bool fused = (what & VP3D_PACK_CONV_T) != 0;
     for (int i = 0; i < p->nb; ++i) {
       if (!w->layers_conv_weight[2 * i] || !w->layers_conv_weight[2 * i + 1])
         return fail(VP3D_ERR_INVALID, "set_weights: missing layers_conv.%d", 2 * i);
+      if (fused) continue;
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i], p->conv[2 * i].w, p->planes,
                                        p->C, p->C, p->taps[i + 1], p->C, p->C, 0, stream));
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i + 1], p->conv[2 * i + 1].w,
                                        p->planes, p->C, p->C, 1, p->C, p->C, 0, stream));
     }
-    CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw, p->C,
-                                     1, p->c_out_pad, p->C, 0, stream));
+    if (!fused)
+      CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw, p->C,
+                                       1, p->c_out_pad, p->C, 0, stream));
     p->conv_packed = true;
   }
   if (what & VP3D_PACK_BN_EVAL) {
@@ -447,7 +451,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
                                 p->c_out_pad, stream));
     p->bn_packed = true;
   }
-  if (what & VP3D_PACK_CONV_T) VP3D_TRY(train_pack_transposed(p, w, stream));
+  if (what & VP3D_PACK_CONV_T)
+    VP3D_TRY(train_pack_transposed(p, w, stream, (what & VP3D_PACK_CONV) != 0));
   return VP3D_OK;
 }
 

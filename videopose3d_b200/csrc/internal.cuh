@@ -100,5 +100,6 @@ bool use_strided(const vp3d_plan* p, int T);
 // rows per sample after each stage: L[0] = rows out of expand, L[i] = rows out of block i
 int layer_rows(const vp3d_plan* p, int T, bool strided, int* L);
 void train_state_destroy(TrainState* t);
-int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream);
+int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream,
+                          bool also_forward);
 }  // namespace vp3d

@@ -207,17 +207,23 @@ DropoutCfg drop_cfg(const TrainState* t, int layer) {
 
 }  // namespace
 
-int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream) {
+// also_forward: the same kernels write the forward packs of the block convs and of shrink (one read
+// of the fp32 weights per optimizer step instead of two).
+int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream,
+                          bool also_forward) {
   VP3D_TRY(ensure_train_state(p));
   TrainState* t = p->train;
   for (int i = 0; i < p->nb; ++i) {
     CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i], t->conv_t[2 * i], p->planes,
-                                       p->C, p->C, p->taps[i + 1], p->C, p->C, stream));
+                                       p->C, p->C, p->taps[i + 1], p->C, p->C, stream,
+                                       also_forward ? p->conv[2 * i].w : nullptr, p->C, p->C));
     CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i + 1], t->conv_t[2 * i + 1],
-                                       p->planes, p->C, p->C, 1, p->C, p->C, stream));
+                                       p->planes, p->C, p->C, 1, p->C, p->C, stream,
+                                       also_forward ? p->conv[2 * i + 1].w : nullptr, p->C, p->C));
   }
   CUDA_TRY(launch_pack_conv_weight_t(w->shrink_weight, t->shrink_t, p->planes, p->c_out_raw, p->C, 1,
-                                     p->C, c_out_pad128(p), stream));
+                                     p->C, c_out_pad128(p), stream,
+                                     also_forward ? p->shrink.w : nullptr, p->c_out_pad, p->C));
   t->packed_t = true;
   return VP3D_OK;
 }

@@ -281,19 +281,30 @@ __global__ void col_sum_f32_kernel(const float* __restrict__ x, long long rows, 
 // w fp32 (c_out, c_in, taps) -> out_t[pl][tap][ci][co] (rows n_pad = padded c_in, cols k_pad = padded
 // c_out).  32 x 32 (co, ci) tiles go through shared memory so that both the reads (ci fastest) and
 // the writes (co fastest) are coalesced.  Padding entries are written as zeros.
+// If `fwd` is non-null the same pass also writes the forward pack fwd[pl][tap][co][ci] (rows
+// fwd_n_pad, cols fwd_k_pad), so one read of the fp32 master feeds both layouts.
 __global__ void __launch_bounds__(256)
 pack_conv_weight_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int planes,
-                          int c_out, int c_in, int taps, int n_pad, int k_pad) {
+                          int c_out, int c_in, int taps, int n_pad, int k_pad,
+                          __nv_bfloat16* __restrict__ fwd, int fwd_n_pad, int fwd_k_pad) {
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const long long plane_elems = (long long)taps * n_pad * k_pad;
+  const long long fwd_plane = (long long)taps * fwd_n_pad * fwd_k_pad;
   for (int tap = 0; tap < taps; ++tap) {
 #pragma unroll
     for (int j = ty; j < 32; j += 8) {
       const int co = co0 + j, ci = ci0 + tx;
-      sm[j][tx] = (co < c_out && ci < c_in) ? __ldg(w + ((long long)co * c_in + ci) * taps + tap)
-                                            : 0.0f;
+      const float v = (co < c_out && ci < c_in)
+                          ? __ldg(w + ((long long)co * c_in + ci) * taps + tap) : 0.0f;
+      sm[j][tx] = v;
+      if (fwd && co < fwd_n_pad && ci < fwd_k_pad) {
+        const long long o = ((long long)tap * fwd_n_pad + co) * fwd_k_pad + ci;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        fwd[o] = hi;
+        if (planes == 2) fwd[fwd_plane + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -388,10 +399,15 @@ cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out
 }
 
 cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
-                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream) {
-  dim3 grid((n_pad + 31) / 32, (k_pad + 31) / 32);
-  pack_conv_weight_t_kernel<<<grid, 256, 0, stream>>>(w, out, planes, c_out, c_in, taps, n_pad,
-                                                      k_pad);
+                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream,
+                                      __nv_bfloat16* fwd, int fwd_n_pad, int fwd_k_pad) {
+  int gx = (n_pad + 31) / 32, gy = (k_pad + 31) / 32;
+  if (fwd) {  // the grid must also cover the forward pack's padding
+    if ((fwd_k_pad + 31) / 32 > gx) gx = (fwd_k_pad + 31) / 32;
+    if ((fwd_n_pad + 31) / 32 > gy) gy = (fwd_n_pad + 31) / 32;
+  }
+  pack_conv_weight_t_kernel<<<dim3(gx, gy), 256, 0, stream>>>(w, out, planes, c_out, c_in, taps,
+                                                              n_pad, k_pad, fwd, fwd_n_pad, fwd_k_pad);
   return cudaGetLastError();
 }
 

@@ -58,7 +58,11 @@ cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out
 
 // Transposed weight pack for dgrad: w fp32 (c_out, c_in, taps) -> bf16 [planes][taps][n_pad][k_pad]
 // with out[pl][tap][ci][co] = w[co][ci][tap]  (rows = input channels, K = output channels).
+// If fwd != nullptr the same pass also writes the forward pack fwd[pl][tap][co][ci] (rows fwd_n_pad,
+// cols fwd_k_pad): one read of the fp32 master feeds both layouts.
 cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
-                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream);
+                                      int c_in, int taps, int n_pad, int k_pad, cudaStream_t stream,
+                                      __nv_bfloat16* fwd = nullptr, int fwd_n_pad = 0,
+                                      int fwd_k_pad = 0);
 
 }  // namespace vp3d
