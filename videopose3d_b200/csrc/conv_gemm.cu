@@ -15,21 +15,28 @@
 
 namespace vp3d {
 
-template <int BLOCK_N, bool RES>
+// WRES ("W resident"): layers whose whole weight slab for one N block fits in 128 KiB of shared
+// memory (the expand conv: K = 128) load it once per CTA and stream only the A tiles; the grid is a
+// multiple of the number of N blocks so that a CTA keeps its N block for all of its tiles.  Without
+// it such a layer re-fetches 64 KiB of W per 32 KiB of A and is bound by the L2 -> SM operand path.
+template <int BLOCK_N, bool RES, bool WRES>
 struct GemmCfg {
+  static_assert(!(RES && WRES), "W-resident variant has no residual path");
   // the RES variant trades one pipeline stage for three residual landing tiles
-  static constexpr int kStages = RES ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 5))
-                                     : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int kStages = WRES ? 3
+                                 : RES ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 5))
+                                       : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStageBytes = WRES ? kABytes : kABytes + kBBytes;
+  static constexpr uint32_t kWResBytes = WRES ? 128u * 1024u : 0u;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
   static constexpr uint32_t kTileBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 tile (16 KiB)
   static constexpr int kResSlots = RES ? 3 : 0;
-  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 6) * 8 + 16;
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 6 + 1) * 8 + 16;
   // pipeline stages + 2 store staging tiles + residual tiles + barriers + 1 KiB alignment slack
   static constexpr uint32_t kSmemBytes =
-      kStages * kStageBytes + (2 + kResSlots) * kTileBytes + kBarBytes + 1024;
+      kStages * kStageBytes + kWResBytes + (2 + kResSlots) * kTileBytes + kBarBytes + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
@@ -75,14 +82,14 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[7] += bf16_hi_to_f(u.w);
 }
 
-template <int BLOCK_N, bool RES>
+template <int BLOCK_N, bool RES, bool WRES>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_z, const ConvGemmArgs p) {
-  using Cfg = GemmCfg<BLOCK_N, RES>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -91,8 +98,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = smem_raw + (base - raw_addr);
 
   const uint32_t smem_a = base;
-  const uint32_t smem_b = base + kStages * Cfg::kABytes;
-  const uint32_t smem_store = base + kStages * Cfg::kStageBytes;  // 2 x 16 KiB, 1024-aligned
+  const uint32_t smem_b = base + kStages * Cfg::kABytes;  // WRES: the resident W slab
+  const uint32_t smem_store = base + kStages * Cfg::kStageBytes + Cfg::kWResBytes;  // 2 x 16 KiB
   const uint32_t smem_res = smem_store + 2 * Cfg::kTileBytes;     // kResSlots x 16 KiB
   const uint32_t bar_base = smem_res + Cfg::kResSlots * Cfg::kTileBytes;
   const uint32_t full_bar = bar_base;
@@ -101,7 +108,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tempty_bar = tfull_bar + 16;
   const uint32_t rfull_bar = tempty_bar + 16;   // 3 residual stages
   const uint32_t rempty_bar = rfull_bar + 24;
-  const uint32_t tmem_slot = rempty_bar + 24;
+  const uint32_t wfull_bar = rempty_bar + 24;   // WRES: the resident W slab has landed
+  const uint32_t tmem_slot = wfull_bar + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
@@ -137,6 +145,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(rfull_bar + s * 8, 1);
       mbar_init(rempty_bar + s * 8, 128);
     }
+    mbar_init(wfull_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -151,6 +160,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      if (WRES) {
+        // every (plane, tap, k-block) tile of this CTA's N block, once
+        const int n_blk = blockIdx.x % p.n_tiles;
+        const int w_tiles = (p.pairs == 3 ? 2 : 1) * p.taps * p.kblocks_per_tap;
+        mbar_expect_tx(wfull_bar, w_tiles * Cfg::kBBytes);
+        for (int wi = 0; wi < w_tiles; ++wi) {
+          const int kb = wi % p.kblocks_per_tap;
+          const int slab = wi / p.kblocks_per_tap;  // w_plane * taps + tap
+          tma_load_2d(&tmap_w, wfull_bar, smem_b + wi * Cfg::kBBytes, kb * kBlockK,
+                      slab * p.n_pad + n_blk * BLOCK_N);
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_blk, sample, row0;
         tile_coords(p, tile, n_blk, sample, row0);
@@ -166,8 +187,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
               tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
                           a_col0 + kb * kBlockK, a_row, sample, a_plane);
-              tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
-                          kb * kBlockK, w_row);
+              if (!WRES)
+                tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
+                            kb * kBlockK, w_row);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -180,6 +202,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
+      if (WRES) mbar_wait(wfull_bar, 0);
+      const int per_pair = p.taps * p.kblocks_per_tap;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);
         tc_fence_after();
@@ -188,7 +212,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(full_bar + stage * 8, phase);
           tc_fence_after();
           const uint64_t desc_a = make_smem_desc_k_sw128(smem_a + stage * Cfg::kABytes);
-          const uint64_t desc_b = make_smem_desc_k_sw128(smem_b + stage * Cfg::kBBytes);
+          // resident slab index: pairs 0 and 1 read the hi plane of W, pair 2 the lo plane
+          const int wi = WRES ? ((it / per_pair == 2 ? per_pair : 0) + it % per_pair) : 0;
+          const uint64_t desc_b = make_smem_desc_k_sw128(
+              WRES ? smem_b + wi * Cfg::kBBytes : smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
@@ -474,15 +501,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BLOCK_N, bool RES>
+template <int BLOCK_N, bool RES, bool WRES>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, RES>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES, WRES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -491,8 +518,9 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
   const int total = m_tiles * args.n_tiles;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < num_sms ? total : num_sms;
-  conv_gemm_kernel<BLOCK_N, RES>
+  int grid = total < num_sms ? total : num_sms;
+  if (WRES) grid = grid / args.n_tiles * args.n_tiles;  // a CTA keeps its N block for every tile
+  conv_gemm_kernel<BLOCK_N, RES, WRES>
       <<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
   return cudaGetLastError();
 }
@@ -502,16 +530,24 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
                              const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
                              int num_sms, cudaStream_t stream) {
   const bool res = args.res_tma != 0 || args.bnb != 0;
+  // W-resident variant: whole weight slab of one N block <= 128 KiB and enough row tiles per CTA
+  const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
+  const long long w_bytes = (long long)(args.pairs == 3 ? 2 : 1) * args.taps * args.kblocks_per_tap *
+                            block_n * kBlockK * 2;
+  const bool wres = !res && block_n >= 128 && w_bytes <= 128 * 1024 &&
+                    (long long)m_tiles * args.n_tiles >= 4LL * num_sms && args.n_tiles <= num_sms;
   switch (block_n) {
     case 256:
-      return res ? launch_impl<256, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<256, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      if (wres) return launch_impl<256, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      return res ? launch_impl<256, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<256, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 128:
-      return res ? launch_impl<128, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<128, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      if (wres) return launch_impl<128, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      return res ? launch_impl<128, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<128, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 64:
-      return res ? launch_impl<64, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<64, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      return res ? launch_impl<64, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_impl<64, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     default:
       return cudaErrorInvalidValue;
   }
