@@ -164,6 +164,61 @@ def cpu_reference_run(n_sample, reps, threads):
     return n_sample * reps / dt, dt
 
 
+def cudnn_reference_arch(dev, x, our_value):
+    """TemporalModel (dense as written, common/model.py:126-138) built from stock torch.nn modules
+    and run by PyTorch/cuDNN on the GPU: fp32 with TF32 convolutions (PyTorch's default) and bf16
+    autocast.  Random weights; only the time matters."""
+    import torch
+    import torch.nn as nn
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.expand = nn.Conv1d(J * F, C, ARC[0], bias=False)
+            self.expand_bn = nn.BatchNorm1d(C)
+            convs, bns, self.pads, d = [], [], [], ARC[0]
+            for w in ARC[1:]:
+                self.pads.append((w - 1) * d // 2)
+                convs += [nn.Conv1d(C, C, w, dilation=d, bias=False), nn.Conv1d(C, C, 1, bias=False)]
+                bns += [nn.BatchNorm1d(C), nn.BatchNorm1d(C)]
+                d *= w
+            self.convs, self.bns = nn.ModuleList(convs), nn.ModuleList(bns)
+            self.shrink = nn.Conv1d(C, J * 3, 1)
+
+        def forward(self, x):
+            n = x.shape[0]
+            x = x.view(n, x.shape[1], -1).permute(0, 2, 1)
+            x = torch.relu(self.expand_bn(self.expand(x)))
+            for i, p in enumerate(self.pads):
+                res = x[:, :, p: x.shape[2] - p]
+                x = torch.relu(self.bns[2 * i](self.convs[2 * i](x)))
+                x = res + torch.relu(self.bns[2 * i + 1](self.convs[2 * i + 1](x)))
+            return self.shrink(x).permute(0, 2, 1).reshape(n, -1, J, 3)
+
+    torch.backends.cudnn.benchmark = True
+    ref = Ref().to(dev).eval()
+    out = {}
+    for name, autocast in (("fp32_tf32", False), ("bf16_autocast", True)):
+        def run():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                return ref(x)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms_per_step": ms, "frames_per_s": N_PER_GPU / ms * 1e3,
+                     "speedup_of_value": our_value / (N_PER_GPU / ms * 1e3)}
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -356,6 +411,14 @@ def run_ours(args, rank, local_rank, world):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cudnn:
+            # informational: the reference architecture executed by stock PyTorch/cuDNN on this same
+            # GPU and batch (the number north_star asks to beat by >= 20x); not the driver's
+            # reference arm, which is the CPU run of --impl reference
+            try:
+                line["cudnn_same_gpu"] = cudnn_reference_arch(dev, xs[0], value)
+            except Exception as e:  # never let the side measurement break the bench line
+                line["cudnn_same_gpu"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -379,6 +442,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cudnn", action="store_true",
+                    help="skip the informational PyTorch/cuDNN measurement of the reference architecture")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -304,12 +304,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // staging tile for this store block: single plane -> double buffered; two planes -> tile 0
         // holds hi, tile 1 holds lo and the previous store must have been read out first.
         const uint32_t buf = two_planes ? 0u : (store_seq & 1u);
-        if (!do_f32 && half == 0) {
-          if (store_leader) {
-            if (two_planes) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-          }
-          epi_bar_sync();
-        }
 
         uint32_t raw[32];
         tmem_ld_32x32(t_addr + chunk * 32, raw);
@@ -366,6 +360,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint32_t hi[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (half == 0) {
+            // The staging tile must have been read out by the bulk store that used it last.  The
+            // wait sits here, after the TMEM load and the epilogue math of this chunk, so that
+            // store latency overlaps that work instead of preceding it.
+            if (store_leader) {
+              if (two_planes) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
+            epi_bar_sync();
+          }
           const uint32_t dst = smem_store + buf * Cfg::kTileBytes + stage_row;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
