@@ -137,6 +137,11 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
       if (m_tiles * (d->n_pad / c) * 2 >= num_sms()) { block_n = c; found = true; break; }
     }
     if (!found) block_n = 64;
+    // Store blocks that need two auxiliary tiles (hi+lo residual, or residual + the Z tile of the
+    // fused BatchNorm backward) only get a second prefetch stage next to 128-wide tiles; those
+    // launches are epilogue-bound, so the narrower MMA costs nothing.
+    const int aux_tiles = (d->res ? (d->res_planes > 0 ? d->res_planes : 1) : 0) + (d->bnb_z ? 1 : 0);
+    if (aux_tiles >= 2 && block_n == 256 && d->n_pad % 128 == 0) block_n = 128;
   }
 
   CUtensorMap ma, mw;

@@ -32,8 +32,10 @@ struct GemmCfg {
   static constexpr uint32_t kWResBytes = WRES ? 128u * 1024u : 0u;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
   static constexpr uint32_t kTileBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 tile (16 KiB)
-  static constexpr int kResSlots = RES ? 3 : 0;
-  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 6 + 1) * 8 + 16;
+  // auxiliary (residual / Z) landing tiles: 3 next to 128x256 tiles, 4 next to narrower ones, so
+  // that two-tile store blocks (hi+lo residual, or residual + Z) still get two stages in flight
+  static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 8 + 1) * 8 + 16;
   // pipeline stages + 2 store staging tiles + residual tiles + barriers + 1 KiB alignment slack
   static constexpr uint32_t kSmemBytes =
       kStages * kStageBytes + kWResBytes + (2 + kResSlots) * kTileBytes + kBarBytes + 1024;
@@ -106,9 +108,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t empty_bar = bar_base + kStages * 8;
   const uint32_t tfull_bar = bar_base + 2 * kStages * 8;
   const uint32_t tempty_bar = tfull_bar + 16;
-  const uint32_t rfull_bar = tempty_bar + 16;   // 3 residual stages
-  const uint32_t rempty_bar = rfull_bar + 24;
-  const uint32_t wfull_bar = rempty_bar + 24;   // WRES: the resident W slab has landed
+  const uint32_t rfull_bar = tempty_bar + 16;   // up to 4 auxiliary stages
+  const uint32_t rempty_bar = rfull_bar + 32;
+  const uint32_t wfull_bar = rempty_bar + 32;   // WRES: the resident W slab has landed
   const uint32_t tmem_slot = wfull_bar + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
@@ -123,7 +125,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // BatchNorm-backward reductions, the Z tile.  Three 16 KiB slots -> 3 / tiles stages in flight.
   const bool has_res = (p.flags & kEpiResidual) != 0;
   const int aux_tiles = (has_res ? p.res_planes : 0) + (p.bnb ? 1 : 0);
-  const int res_stages = aux_tiles > 0 ? 3 / aux_tiles : 1;
+  const int res_stages = (aux_tiles > 0 && Cfg::kResSlots >= aux_tiles) ? Cfg::kResSlots / aux_tiles : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -141,7 +143,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar + s * 8, 1);
       mbar_init(tempty_bar + s * 8, 128);
     }
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(rfull_bar + s * 8, 1);
       mbar_init(rempty_bar + s * 8, 128);
     }
