@@ -142,6 +142,8 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     // launches are epilogue-bound, so the narrower MMA costs nothing.
     const int aux_tiles = (d->res ? (d->res_planes > 0 ? d->res_planes : 1) : 0) + (d->bnb_z ? 1 : 0);
     if (aux_tiles >= 2 && block_n == 256 && d->n_pad % 128 == 0) block_n = 128;
+    // (the residual kernel variant has no 256-wide, two-output-plane instantiation)
+    if (aux_tiles >= 1 && d->out_planes == 2 && block_n == 256) block_n = 128;
   }
 
   CUtensorMap ma, mw;

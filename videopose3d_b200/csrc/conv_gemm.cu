@@ -1,14 +1,17 @@
 // tcgen05 implicit-GEMM kernel for the temporal convolutions.  See conv_gemm.cuh for the math.
 //
-// CTA = 256 threads, persistent over output tiles (128 rows x BLOCK_N channels):
+// CTA = 384 threads, persistent over output tiles (128 rows x BLOCK_N channels):
 //   warp 0 lane 0 : TMA producer  (A tile 128x64 bf16 + W tile BLOCK_Nx64 bf16 per k-block)
 //   warp 1 lane 0 : tcgen05.mma issuer (4 x K=16 MMAs per k-block, accumulator in TMEM)
 //   warp 2        : TMEM allocator / deallocator
-//   warp 3 lane 0 : residual producer (RES variant): TMA-loads the 128x64 residual tile of every
-//                   64-column store block into shared memory ahead of the epilogue
-//   warps 4..7    : epilogue: tcgen05.ld -> BN affine / ReLU / residual / batch sums in registers
-//                   -> bf16 pack into a SWIZZLE_128B staging tile in shared memory -> TMA store
-//                   (coalesced 128-byte rows, clipped at the tensor edge by the tensor map)
+//   warp 3 lane 0 : auxiliary producer (RES variant): TMA-loads the 128x64 residual tile(s) / the Z
+//                   tile of every 64-column store block into shared memory ahead of the epilogue
+//   warps 4..11   : epilogue, two groups of four warps (each group covers the 128 TMEM lanes); the
+//                   64-column store blocks of a tile alternate between the groups, so two epilogue
+//                   warps share every SM sub-partition and hide each other's latencies:
+//                   tcgen05.ld -> BN affine / ReLU / residual / batch sums in registers -> bf16 pack
+//                   into the group's SWIZZLE_128B staging tile(s) -> TMA store (coalesced 128-byte
+//                   rows, clipped at the tensor edge by the tensor map)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
@@ -17,28 +20,29 @@ namespace vp3d {
 
 // WRES ("W resident"): layers whose whole weight slab for one N block fits in 128 KiB of shared
 // memory (the expand conv: K = 128) load it once per CTA and stream only the A tiles; the grid is a
-// multiple of the number of N blocks so that a CTA keeps its N block for all of its tiles.  Without
-// it such a layer re-fetches 64 KiB of W per 32 KiB of A and is bound by the L2 -> SM operand path.
-template <int BLOCK_N, bool RES, bool WRES>
+// multiple of the number of N blocks so that a CTA keeps its N block for all of its tiles.
+// OUT2: two output planes (hi, lo) -> each epilogue group needs two staging tiles; the extra 32 KiB
+// come out of the operand pipeline.
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
 struct GemmCfg {
   static_assert(!(RES && WRES), "W-resident variant has no residual path");
-  // the RES variant trades one pipeline stage for three residual landing tiles
-  static constexpr int kStages = WRES ? 3
-                                 : RES ? ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 5))
-                                       : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = WRES ? kABytes : kABytes + kBBytes;
   static constexpr uint32_t kWResBytes = WRES ? 128u * 1024u : 0u;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
   static constexpr uint32_t kTileBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 tile (16 KiB)
+  static constexpr int kStoreTiles = OUT2 ? 4 : 2;          // one (hi[, lo]) set per epilogue group
   // auxiliary (residual / Z) landing tiles: 3 next to 128x256 tiles, 4 next to narrower ones, so
   // that two-tile store blocks (hi+lo residual, or residual + Z) still get two stages in flight
   static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
+  static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
+  // as many operand stages as fit below 224 KiB, at most 8
+  static constexpr int kStagesFit = (224u * 1024u - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static_assert(kStages >= 2, "not enough shared memory for the operand pipeline");
   static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 8 + 1) * 8 + 16;
-  // pipeline stages + 2 store staging tiles + residual tiles + barriers + 1 KiB alignment slack
-  static constexpr uint32_t kSmemBytes =
-      kStages * kStageBytes + kWResBytes + (2 + kResSlots) * kTileBytes + kBarBytes + 1024;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedBytes + kBarBytes + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
@@ -54,8 +58,8 @@ __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int
   }
 }
 
-__device__ __forceinline__ void epi_bar_sync() {
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+__device__ __forceinline__ void group_bar_sync(uint32_t id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");  // the four warps of one epilogue group
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
@@ -84,15 +88,16 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[7] += bf16_hi_to_f(u.w);
 }
 
-template <int BLOCK_N, bool RES, bool WRES>
-__global__ void __launch_bounds__(256, 1)
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+__global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_z, const ConvGemmArgs p) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kBlocksPerTile = BLOCK_N / 64;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -101,8 +106,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + kStages * Cfg::kABytes;  // WRES: the resident W slab
-  const uint32_t smem_store = base + kStages * Cfg::kStageBytes + Cfg::kWResBytes;  // 2 x 16 KiB
-  const uint32_t smem_res = smem_store + 2 * Cfg::kTileBytes;     // kResSlots x 16 KiB
+  const uint32_t smem_store = base + kStages * Cfg::kStageBytes + Cfg::kWResBytes;
+  const uint32_t smem_res = smem_store + Cfg::kStoreTiles * Cfg::kTileBytes;
   const uint32_t bar_base = smem_res + Cfg::kResSlots * Cfg::kTileBytes;
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + kStages * 8;
@@ -122,10 +127,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int total_tiles = m_tiles * p.n_tiles;
   const int k_iters = p.pairs * p.taps * p.kblocks_per_tap;
   // auxiliary tiles per 64-column store block: the residual plane(s) and, for the fused
-  // BatchNorm-backward reductions, the Z tile.  Three 16 KiB slots -> 3 / tiles stages in flight.
+  // BatchNorm-backward reductions, the Z tile.  kResSlots / tiles stages are in flight.
   const bool has_res = (p.flags & kEpiResidual) != 0;
   const int aux_tiles = (has_res ? p.res_planes : 0) + (p.bnb ? 1 : 0);
-  const int res_stages = (aux_tiles > 0 && Cfg::kResSlots >= aux_tiles) ? Cfg::kResSlots / aux_tiles : 1;
+  const int res_stages =
+      (aux_tiles > 0 && Cfg::kResSlots >= aux_tiles) ? Cfg::kResSlots / aux_tiles : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -141,11 +147,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s * 8, 1);
-      mbar_init(tempty_bar + s * 8, 128);
+      mbar_init(tempty_bar + s * 8, 256);  // both epilogue groups release an accumulator stage
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(rfull_bar + s * 8, 1);
-      mbar_init(rempty_bar + s * 8, 128);
+      mbar_init(rempty_bar + s * 8, 128);  // one group consumes an auxiliary stage
     }
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
@@ -231,13 +237,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------------ residual producer
+    // ------------------------------------------------------------ auxiliary-tile producer
     if (RES && lane == 0) {
       uint32_t rs = 0, rphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_blk, sample, row0;
         tile_coords(p, tile, n_blk, sample, row0);
-        for (int sb = 0; sb < BLOCK_N / 64; ++sb) {
+        for (int sb = 0; sb < kBlocksPerTile; ++sb) {
           const int col = n_blk * BLOCK_N + sb * 64;
           const bool res_here = has_res && col >= p.res_col_begin && col < p.res_col_begin + p.res_cols;
           if (!res_here && !p.bnb) continue;
@@ -257,22 +263,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (two groups)
+    const int eg = (warp - 4) >> 2;   // epilogue group 0 / 1
+    const int ew = warp & 3;          // TMEM lane quarter this warp may access
     const int r_in_tile = ew * 32 + lane;
-    const bool store_leader = (threadIdx.x == 128);
+    const bool store_leader = (threadIdx.x == 128u + 128u * eg);
+    const uint32_t bar_id = 1 + eg;
     uint32_t acc = 0, acc_phase = 0;
-    uint32_t store_seq = 0;
-    uint32_t rs = 0, rphase = 0;
+    uint32_t gblock = 0;              // store blocks seen so far (both groups count all of them)
+    uint32_t ablock = 0;              // auxiliary stages seen so far
     const bool do_relu = p.flags & kEpiRelu;
     const bool do_res = p.flags & kEpiResidual;
     const bool do_stats = p.flags & kEpiStats;
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
-    const bool two_planes = p.out_planes == 2;
+    const bool two_planes = OUT2 && p.out_planes == 2;
     // swizzled tile address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
     const uint32_t stage_row = r_in_tile * 128;
     const uint32_t sw = r_in_tile & 7;
+    // this group's staging tile(s): [hi] or [hi, lo]
+    const uint32_t my_store = smem_store + eg * (OUT2 ? 2 : 1) * Cfg::kTileBytes;
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int n_blk, sample, row0;
@@ -293,200 +303,200 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         res_row = (long long)rsmp * p.res_rows_per_sample + in_sample;
       }
 
+      // Both groups wait for the accumulator even when a tile holds no block for one of them: the
+      // release below must not run ahead of the MMAs that refill this TMEM stage.
       mbar_wait(tfull_bar + acc * 8, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        const int half = chunk & 1;  // which 32-column half of the 64-column store block
-        const int c0 = n_blk * BLOCK_N + chunk * 32;
-        const int cb = c0 - half * 32;  // first column of the store block
+      for (int sb = 0; sb < kBlocksPerTile; ++sb, ++gblock) {
+        const int cb = n_blk * BLOCK_N + sb * 64;  // first column of the store block
         const bool res_here = do_res && cb >= p.res_col_begin && cb < p.res_col_begin + p.res_cols;
-        // staging tile for this store block: single plane -> double buffered; two planes -> tile 0
-        // holds hi, tile 1 holds lo and the previous store must have been read out first.
-        const uint32_t buf = two_planes ? 0u : (store_seq & 1u);
-
-        uint32_t raw[32];
-        tmem_ld_32x32(t_addr + chunk * 32, raw);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-
-        if (do_affine) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
-            v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
-            v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-            v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
-            v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-          }
-        }
-        if (do_relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
         const bool aux_here = RES && (res_here || p.bnb);
-        if (RES) {
-          if (aux_here && half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
-          if (res_here) {
-            for (int pl = 0; pl < p.res_planes; ++pl) {
-              const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
+        const uint32_t rs = aux_here ? ablock % (uint32_t)res_stages : 0u;
+        const uint32_t rphase = aux_here ? (ablock / (uint32_t)res_stages) & 1u : 0u;
+        if (aux_here) ++ablock;
+        if ((gblock & 1u) != (uint32_t)eg) continue;  // the other group owns this store block
+
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int chunk = sb * 2 + half;
+          const int c0 = cb + half * 32;
+          uint32_t raw[32];
+          tmem_ld_32x32(t_addr + chunk * 32, raw);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+
+          if (do_affine) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+              v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
+              v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+              v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+              v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
             }
           }
-        } else if (res_here && res_ok) {
-          const __nv_bfloat16* rp = p.res + res_row * p.res_ld + (c0 - p.res_col_begin);
+          if (do_relu) {
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
-            if (pl < p.res_planes) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (RES) {
+            if (aux_here && half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
+            if (res_here) {
+              for (int pl = 0; pl < p.res_planes; ++pl) {
+                const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) add_bf16x8(v + q * 8, __ldg(r4 + q));
+                for (int q = 0; q < 4; ++q)
+                  add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
+              }
+            }
+          } else if (res_here && res_ok) {
+            const __nv_bfloat16* rp = p.res + res_row * p.res_ld + (c0 - p.res_col_begin);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              if (pl < p.res_planes) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) add_bf16x8(v + q * 8, __ldg(r4 + q));
+              }
             }
           }
-        }
-        if (do_f32) {
-          if (valid) {
-            float* op = p.out_f32 + out_row * p.out_f32_ld + c0;
+          if (do_f32) {
+            if (valid) {
+              float* op = p.out_f32 + out_row * p.out_f32_ld + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.n_valid) op[j] = v[j];
-          }
-        } else {
-          uint32_t hi[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (half == 0) {
-            // The staging tile must have been read out by the bulk store that used it last.  The
-            // wait sits here, after the TMEM load and the epilogue math of this chunk, so that
-            // store latency overlaps that work instead of preceding it.
-            if (store_leader) {
-              if (two_planes) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.n_valid) op[j] = v[j];
             }
-            epi_bar_sync();
-          }
-          const uint32_t dst = smem_store + buf * Cfg::kTileBytes + stage_row;
+          } else {
+            uint32_t hi[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            st_shared_v4(dst + (((half * 4 + q) ^ sw) << 4), hi[4 * q], hi[4 * q + 1],
-                         hi[4 * q + 2], hi[4 * q + 3]);
-          if (two_planes) {
-            uint32_t lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float r0 = v[2 * j] - bf16_lo_to_f(hi[j]);
-              const float r1 = v[2 * j + 1] - bf16_hi_to_f(hi[j]);
-              lo[j] = pack_bf16x2(r0, r1);
+            for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            if (half == 0) {
+              // This group's staging tile(s) must have been read out by the bulk store that used
+              // them last (two store blocks ago).  The wait sits after the TMEM load and the math
+              // of this chunk so that store latency overlaps that work.
+              if (store_leader) tma_store_wait_read<0>();
+              group_bar_sync(bar_id);
             }
-            const uint32_t dst_lo = smem_store + Cfg::kTileBytes + stage_row;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              st_shared_v4(dst_lo + (((half * 4 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1],
-                           lo[4 * q + 2], lo[4 * q + 3]);
-          }
-          if (half == 1) {
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
-            epi_bar_sync();
-            if (store_leader) {
-              tma_store_4d(&tmap_out, smem_store + buf * Cfg::kTileBytes, cb, row0, sample, 0);
-              if (two_planes)
-                tma_store_4d(&tmap_out, smem_store + Cfg::kTileBytes, cb, row0, sample, 1);
-              tma_store_commit();
+              st_shared_v4(my_store + stage_row + (((half * 4 + q) ^ sw) << 4), hi[4 * q],
+                           hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            if (two_planes) {
+              uint32_t lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float r0 = v[2 * j] - bf16_lo_to_f(hi[j]);
+                const float r1 = v[2 * j + 1] - bf16_hi_to_f(hi[j]);
+                lo[j] = pack_bf16x2(r0, r1);
+              }
+              const uint32_t dst_lo = my_store + Cfg::kTileBytes + stage_row;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                st_shared_v4(dst_lo + (((half * 4 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1],
+                             lo[4 * q + 2], lo[4 * q + 3]);
             }
-            ++store_seq;
-          }
-        }
-        if (RES && p.bnb) {
-          // dY = G(as stored) * dropmask/(1-p) * [Z*scale+shift > 0]; sums over this warp's 32 rows
-          float zf[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) zf[j] = 0.0f;
-          const uint32_t zsrc = smem_res + (rs * aux_tiles + aux_tiles - 1) * Cfg::kTileBytes + stage_row;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            add_bf16x8(zf + q * 8, ld_shared_v4(zsrc + (((half * 4 + q) ^ sw) << 4)));
-          const int ch0 = c0 % p.bnb_c;
-          const bool drop = p.bnb_p > 0.0f;
-          const uint32_t thresh = (uint32_t)(p.bnb_p * 65536.0f);
-          const float inv_keep = drop ? 1.0f / (1.0f - p.bnb_p) : 1.0f;
-          const unsigned long long elem0 = (unsigned long long)out_row * p.out_ld + c0;
-          const uint32_t key = p.bnb_seed_lo ^ (p.bnb_seed_hi * 0x7F4A7C15u) ^
-                               (p.bnb_layer * 0x632BE5ABu) ^
-                               ((uint32_t)((elem0 >> 1) >> 32) * 0x85EBCA77u);
-          const uint32_t pbase = (uint32_t)(elem0 >> 1);
-          float s[32], q2[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float m0 = 1.0f, m1 = 1.0f;
-            if (drop) {
-              uint32_t h = (pbase + (j >> 1)) * 0x9E3779B1u + key;
-              h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-              m0 = ((h & 0xFFFFu) >= thresh) ? inv_keep : 0.0f;
-              m1 = ((h >> 16) >= thresh) ? inv_keep : 0.0f;
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int jj = j + e;
-              // gradient exactly as the next pass will read it back (bf16-rounded)
-              const float g = __bfloat162float(__float2bfloat16_rn(v[jj]));
-              const float y = fmaf(zf[jj], __ldg(p.bnb_scale + ch0 + jj), __ldg(p.bnb_shift + ch0 + jj));
-              float dy = (valid && y > 0.0f) ? g : 0.0f;
-              dy *= e ? m1 : m0;
-              s[jj] = dy;
-              q2[jj] = dy * (zf[jj] - __ldg(p.bnb_mean + ch0 + jj));
+            if (half == 1) {
+              fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+              group_bar_sync(bar_id);
+              if (store_leader) {
+                tma_store_4d(&tmap_out, my_store, cb, row0, sample, 0);
+                if (two_planes) tma_store_4d(&tmap_out, my_store + Cfg::kTileBytes, cb, row0, sample, 1);
+                tma_store_commit();
+              }
             }
           }
+          if (RES && p.bnb) {
+            // dY = G(as stored) * dropmask/(1-p) * [Z*scale+shift > 0]; sums over this warp's 32 rows
+            float zf[32];
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = lane & off;
+            for (int j = 0; j < 32; ++j) zf[j] = 0.0f;
+            const uint32_t zsrc =
+                smem_res + (rs * aux_tiles + aux_tiles - 1) * Cfg::kTileBytes + stage_row;
 #pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send_s = upper ? s[i] : s[i + off];
-              const float keep_s = upper ? s[i + off] : s[i];
-              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-              const float send_q = upper ? q2[i] : q2[i + off];
-              const float keep_q = upper ? q2[i + off] : q2[i];
-              q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            for (int q = 0; q < 4; ++q)
+              add_bf16x8(zf + q * 8, ld_shared_v4(zsrc + (((half * 4 + q) ^ sw) << 4)));
+            const int ch0 = c0 % p.bnb_c;
+            const bool drop = p.bnb_p > 0.0f;
+            const uint32_t thresh = (uint32_t)(p.bnb_p * 65536.0f);
+            const float inv_keep = drop ? 1.0f / (1.0f - p.bnb_p) : 1.0f;
+            const unsigned long long elem0 = (unsigned long long)out_row * p.out_ld + c0;
+            const uint32_t key = p.bnb_seed_lo ^ (p.bnb_seed_hi * 0x7F4A7C15u) ^
+                                 (p.bnb_layer * 0x632BE5ABu) ^
+                                 ((uint32_t)((elem0 >> 1) >> 32) * 0x85EBCA77u);
+            const uint32_t pbase = (uint32_t)(elem0 >> 1);
+            float s[32], q2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float m0 = 1.0f, m1 = 1.0f;
+              if (drop) {
+                uint32_t h = (pbase + (j >> 1)) * 0x9E3779B1u + key;
+                h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+                m0 = ((h & 0xFFFFu) >= thresh) ? inv_keep : 0.0f;
+                m1 = ((h >> 16) >= thresh) ? inv_keep : 0.0f;
+              }
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int jj = j + e;
+                // gradient exactly as the next pass will read it back (bf16-rounded)
+                const float g = __bfloat162float(__float2bfloat16_rn(v[jj]));
+                const float y = fmaf(zf[jj], __ldg(p.bnb_scale + ch0 + jj), __ldg(p.bnb_shift + ch0 + jj));
+                float dy = (valid && y > 0.0f) ? g : 0.0f;
+                dy *= e ? m1 : m0;
+                s[jj] = dy;
+                q2[jj] = dy * (zf[jj] - __ldg(p.bnb_mean + ch0 + jj));
+              }
             }
-          }
-          atomicAdd(p.bnb_sums + ch0 + lane, s[0]);
-          atomicAdd(p.bnb_sums + p.bnb_c + ch0 + lane, q2[0] * __ldg(p.bnb_invstd + ch0 + lane));
-        }
-        if (RES && aux_here && half == 1) {
-          mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the auxiliary stage
-          if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
-        }
-        if (do_stats) {
-          // Per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce,
-          // 31 shuffles per statistic; afterwards lane j owns channel c0 + j.
-          float s[32], q[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = valid ? v[j] : 0.0f;
-            s[j] = x;
-            q[j] = x * x;
-          }
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = lane & off;
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = lane & off;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send_s = upper ? s[i] : s[i + off];
-              const float keep_s = upper ? s[i + off] : s[i];
-              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-              const float send_q = upper ? q[i] : q[i + off];
-              const float keep_q = upper ? q[i + off] : q[i];
-              q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              for (int i = 0; i < off; ++i) {
+                const float send_s = upper ? s[i] : s[i + off];
+                const float keep_s = upper ? s[i + off] : s[i];
+                s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                const float send_q = upper ? q2[i] : q2[i + off];
+                const float keep_q = upper ? q2[i + off] : q2[i];
+                q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
             }
+            atomicAdd(p.bnb_sums + ch0 + lane, s[0]);
+            atomicAdd(p.bnb_sums + p.bnb_c + ch0 + lane, q2[0] * __ldg(p.bnb_invstd + ch0 + lane));
           }
-          atomicAdd(p.stats + c0 + lane, s[0]);
-          atomicAdd(p.stats + p.n_pad + c0 + lane, q[0]);
+          if (RES && aux_here && half == 1)
+            mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the auxiliary stage
+          if (do_stats) {
+            // Per-channel sum / sum of squares over this warp's 32 rows: butterfly transpose-reduce,
+            // 31 shuffles per statistic; afterwards lane j owns channel c0 + j.
+            float s[32], q[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = valid ? v[j] : 0.0f;
+              s[j] = x;
+              q[j] = x * x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = lane & off;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send_s = upper ? s[i] : s[i + off];
+                const float keep_s = upper ? s[i + off] : s[i];
+                s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                const float send_q = upper ? q[i] : q[i + off];
+                const float keep_q = upper ? q[i + off] : q[i];
+                q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
+            }
+            atomicAdd(p.stats + c0 + lane, s[0]);
+            atomicAdd(p.stats + p.n_pad + c0 + lane, q[0]);
+          }
         }
       }
       tc_fence_before();
@@ -506,15 +516,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BLOCK_N, bool RES, bool WRES>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES, WRES>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -525,9 +535,18 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   if (total <= 0) return cudaSuccess;
   int grid = total < num_sms ? total : num_sms;
   if (WRES) grid = grid / args.n_tiles * args.n_tiles;  // a CTA keeps its N block for every tile
-  conv_gemm_kernel<BLOCK_N, RES, WRES>
-      <<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
+  conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2>
+      <<<grid, 384, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
   return cudaGetLastError();
+}
+
+template <int BLOCK_N, bool RES, bool WRES>
+static cudaError_t launch_planes(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
+                                 const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
+                                 int num_sms, cudaStream_t stream) {
+  if (args.out_planes == 2 && !(args.flags & kEpiOutF32))
+    return launch_impl<BLOCK_N, RES, WRES, true>(a, w, o, r, z, args, num_sms, stream);
+  return launch_impl<BLOCK_N, RES, WRES, false>(a, w, o, r, z, args, num_sms, stream);
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
@@ -543,16 +562,20 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
                     (long long)m_tiles * args.n_tiles >= 4LL * num_sms && args.n_tiles <= num_sms;
   switch (block_n) {
     case 256:
-      if (wres) return launch_impl<256, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
-      return res ? launch_impl<256, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<256, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      if (wres) return launch_planes<256, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      if (res) {
+        // (two output planes next to a TMA residual always run on 128-wide tiles, see run_conv)
+        if (args.out_planes == 2) return cudaErrorInvalidConfiguration;
+        return launch_impl<256, true, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      }
+      return launch_planes<256, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 128:
-      if (wres) return launch_impl<128, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
-      return res ? launch_impl<128, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<128, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      if (wres) return launch_planes<128, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      return res ? launch_planes<128, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_planes<128, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 64:
-      return res ? launch_impl<64, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
-                 : launch_impl<64, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      return res ? launch_planes<64, true, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream)
+                 : launch_planes<64, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     default:
       return cudaErrorInvalidValue;
   }
