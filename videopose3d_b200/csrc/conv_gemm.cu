@@ -35,7 +35,10 @@ struct GemmCfg {
   static constexpr int kStoreTiles = OUT2 ? 4 : 2;          // one (hi[, lo]) set per epilogue group
   // auxiliary (residual / Z) landing tiles: 3 next to 128x256 tiles, 4 next to narrower ones, so
   // that two-tile store blocks (hi+lo residual, or residual + Z) still get two stages in flight
-  static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
+  // (with two output planes the four staging tiles already take 64 KiB: one auxiliary stage only,
+  // the second epilogue group covers the exposed load latency, and the operand pipeline keeps its
+  // depth)
+  static constexpr int kResSlots = RES ? (OUT2 ? 2 : (BLOCK_N == 256 ? 3 : 4)) : 0;
   static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
   // as many operand stages as fit below 224 KiB, at most 8
   static constexpr int kStagesFit = (224u * 1024u - kFixedBytes) / kStageBytes;
