@@ -38,7 +38,7 @@ struct GemmCfg {
   // (with two output planes the four staging tiles already take 64 KiB: one auxiliary stage only,
   // the second epilogue group covers the exposed load latency, and the operand pipeline keeps its
   // depth)
-  static constexpr int kResSlots = RES ? (OUT2 ? 2 : (BLOCK_N == 256 ? 3 : 4)) : 0;
+  static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
   static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
   // as many operand stages as fit below 224 KiB, at most 8
   static constexpr int kStagesFit = (224u * 1024u - kFixedBytes) / kStageBytes;
@@ -318,7 +318,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool res_here = do_res && cb >= p.res_col_begin && cb < p.res_col_begin + p.res_cols;
         const bool aux_here = RES && (res_here || p.bnb);
         const uint32_t rs = aux_here ? ablock % (uint32_t)res_stages : 0u;
-        const uint32_t rphase = aux_here ? (ablock / (uint32_t)res_stages) & 1u : 0u;
+        const uint32_t ruse = aux_here ? ablock / (uint32_t)res_stages : 0u;  // n-th use of stage rs
+        const uint32_t rphase = ruse & 1u;
         if (aux_here) ++ablock;
         if ((gblock & 1u) != (uint32_t)eg) continue;  // the other group owns this store block
 
@@ -349,7 +350,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
           if (RES) {
-            if (aux_here && half == 0) mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
+            if (aux_here && half == 0) {
+              // The previous use of this stage may belong to the other epilogue group.  A parity
+              // wait only tells "one phase ahead" from "done", so first make sure that use has been
+              // released (which implies its fill completed); then the fill wait is unambiguous.
+              if (ruse > 0) mbar_wait(rempty_bar + rs * 8, (ruse - 1) & 1u);
+              mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
+            }
             if (res_here) {
               for (int pl = 0; pl < p.res_planes; ++pl) {
                 const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
