@@ -42,6 +42,12 @@ FLOPS_PER_SAMPLE_DENSE = 5217.8e6     # what the reference executes as written (
 # dominant kernel: block-1 conv, rows = N*27, K = 3*1024, N = 1024
 DOMINANT_LAUNCH_INDEX = 2             # pack_input, expand, [block-1 conv], ...
 DOMINANT_FLOPS_PER_LAUNCH = 2.0 * (N_PER_GPU * 27) * 3072 * 1024
+# its compulsory HBM bytes: A 27648x3072 bf16 + W 1024x3072 bf16 + out 27648x1024 bf16
+DOMINANT_ALGORITHMIC_BYTES = 2.0 * (N_PER_GPU * 27 * 3072 + 1024 * 3072 + N_PER_GPU * 27 * 1024)
+# DRAM bytes of that launch from the committed `ncu --set full` capture of the final build
+# (176.2 MB read + 34.6 MB written; below the algorithmic bytes because part of the freshly
+# written input is still L2-resident)
+DOMINANT_DRAM_BYTES_NCU = 210.8e6
 
 
 def load_peaks():
@@ -401,7 +407,10 @@ def run_ours(args, rank, local_rank, world):
             "launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_tf / peak_tf, "traffic": DOMINANT_DRAM_BYTES_NCU,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
+                                           "of this launch (profiles/r1l_ncu_full_eval_mixed.csv, ID 2)",
+                         "algorithmic_bytes": DOMINANT_ALGORITHMIC_BYTES, "peak_source": peak_src,
                          "kernel": "conv_gemm_kernel<256> block-1 3-tap conv (M=27648,K=3072,N=1024)",
                          "flops_per_launch": DOMINANT_FLOPS_PER_LAUNCH, "ms_per_launch": dom_ms,
                          "launches_timed": cnt.value},
@@ -426,6 +435,133 @@ def run_ours(args, rank, local_rank, world):
     return line
 
 
+def run_input_pipeline(args):
+    """the training input pipeline.  Device-resident generator
+    (videopose3d_b200.generators.ChunkedGenerator -> vp3d_gather_windows) against the CPU port of
+    the reference's ChunkedGenerator + cast + H2D copy (generators.py:99-160, run.py:401-406), on
+    an H36M-shaped synthetic stream, and the training step fed either way."""
+    import numpy as np
+    import torch
+    import videopose3d_b200 as vp
+    from videopose3d_b200 import generators as G
+    from oracle import generator_oracle as gorc  # CPU baseline leg only
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    rng = np.random.RandomState(0)
+    n_seq = args.sequences
+    lens = rng.randint(1000, 6001, size=n_seq)
+    p2 = [rng.uniform(-1, 1, (n, J, F)).astype(np.float32) for n in lens]
+    p3 = [rng.normal(0, 0.5, (n, J, 3)).astype(np.float32) for n in lens]
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    kw = dict(pad=121, causal_shift=0, shuffle=True, random_seed=1234, augment=True, kps_left=left,
+              kps_right=right, joints_left=left, joints_right=right)
+    t0 = time.perf_counter()
+    gen = G.ChunkedGenerator(N_PER_GPU, None, p3, p2, 1, device=dev, **kw)
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t0
+    it = gen.next_epoch()
+    t0 = time.perf_counter()
+    next(it)
+    torch.cuda.synchronize()
+    epoch_start_s = time.perf_counter() - t0   # permutation draw + table upload + first batch
+    for _ in range(max(3, args.warmup)):
+        next(it)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        batch = next(it)
+        b.record()
+    torch.cuda.synchronize()
+    gather_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    out_bytes = N_PER_GPU * (T * J * F + J * 3) * 4
+    algo_bytes = 2 * out_bytes              # every output element is read once and written once
+    _, peak_gbs, peak_src = load_peaks()
+    # host wall clock per batch of the device generator (Python + 2 launches, GPU idle otherwise)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch = next(it)
+    torch.cuda.synchronize()
+    dev_wall_ms = (time.perf_counter() - t0) / args.steps * 1e3
+
+    # CPU port of the reference path: generator batch -> float32 -> pinned -> H2D
+    orc = gorc.ChunkedGeneratorOracle(N_PER_GPU, None, p3, p2, 1, **kw)
+    oit = orc.next_epoch()
+    next(oit)
+    cpu_batches = 4
+    t0 = time.perf_counter()
+    for _ in range(cpu_batches):
+        _, b3, b2 = next(oit)
+    cpu_gen_ms = (time.perf_counter() - t0) / cpu_batches * 1e3
+    t0 = time.perf_counter()
+    for _ in range(cpu_batches):
+        _, b3, b2 = next(oit)
+        x = torch.from_numpy(b2.astype("float32")).cuda()
+        y = torch.from_numpy(b3.astype("float32")).cuda()
+    torch.cuda.synchronize()
+    cpu_fed_ms = (time.perf_counter() - t0) / cpu_batches * 1e3
+
+    # training step (Optimized1f, fwd + bwd + Adam/amsgrad) fed by either pipeline
+    model = vp.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, channels=C).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True)
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = torch.mean(torch.norm(model(x) - y, dim=-1))
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        _, y, x = next(it)
+        step(x, y)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, y, x = next(it)
+        loss = step(x, y)
+    loss.item()
+    torch.cuda.synchronize()
+    train_dev_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    host_steps = 4
+    t0 = time.perf_counter()
+    for _ in range(host_steps):
+        _, b3, b2 = next(oit)
+        loss = step(torch.from_numpy(b2.astype("float32")).cuda(),
+                    torch.from_numpy(b3.astype("float32")).cuda())
+    loss.item()
+    torch.cuda.synchronize()
+    train_host_ms = (time.perf_counter() - t0) / host_steps * 1e3
+
+    line = {
+        "what": "train_input_pipeline (SURVEY 8 f1)", "n_gpus": 1, "steps": args.steps,
+        "config": {"workload": f"ChunkedGenerator batch 1024 x (243,17,2) + (1,17,3), shuffle + flip "
+                               f"augmentation, {n_seq} sequences of 1000-6000 frames "
+                               f"({int(lens.sum())} frames, {int(lens.sum()) * J * F * 4 / 1e6:.0f} MB of 2-D input)",
+                   "l2": "256 MiB memset between timed gathers"},
+        "device_generator": {"gather_ms_per_batch": gather_ms, "host_wall_ms_per_batch": dev_wall_ms,
+                             "dataset_upload_s": upload_s, "epoch_start_s": epoch_start_s,
+                             "h2d_bytes_per_step": 0, "gpu_launches_per_batch": 2},
+        "roofline": {"bound": "hbm", "achieved": algo_bytes / (gather_ms * 1e-3) / 1e9, "peak": peak_gbs,
+                     "unit": "GB/s", "frac": algo_bytes / (gather_ms * 1e-3) / 1e9 / peak_gbs,
+                     "algorithmic_bytes": algo_bytes, "traffic": None, "peak_source": peak_src,
+                     "kernel": "gather_windows_kernel (2-D windows) + (3-D targets)"},
+        "cpu_baseline": {"generator_ms_per_batch": cpu_gen_ms, "generator_cast_h2d_ms_per_batch": cpu_fed_ms,
+                         "kind": "port", "cores": 1,
+                         "sample": f"{cpu_batches} batches, oracle ChunkedGeneratorOracle (NumPy, single "
+                                   "thread like the reference's Python loop) + astype(float32) + .cuda()"},
+        "train_step_fed_by_device_generator_ms": train_dev_ms,
+        "train_step_fed_by_host_generator_ms": train_host_ms,
+        "train_frames_per_s_device_fed": N_PER_GPU / (train_dev_ms * 1e-3),
+        "train_frames_per_s_host_fed": N_PER_GPU / (train_host_ms * 1e-3),
+    }
+    print(json.dumps(line), flush=True)
+    return line
+
+
 def _visible_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     try:
@@ -444,7 +580,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cudnn", action="store_true",
                     help="skip the informational PyTorch/cuDNN measurement of the reference architecture")
+    ap.add_argument("--input-pipeline", action="store_true",
+                    help="measure the training input pipeline (device generator vs CPU port) instead")
+    ap.add_argument("--sequences", type=int, default=600)
     args = ap.parse_args()
+    if args.input_pipeline:
+        if args.steps == 200:
+            args.steps = 50
+        run_input_pipeline(args)
+        return
     if args.warmup < 3:
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))

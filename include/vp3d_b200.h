@@ -239,6 +239,37 @@ typedef struct {
 
 int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream);
 
+/* ---- device-resident batch gather --------------------------------------------
+ * Replaces the per-chunk Python loops of the reference generators:
+ *   common/generators.py:99-160  ChunkedGenerator.next_epoch   (training windows)
+ *   common/generators.py:213-240 UnchunkedGenerator.next_epoch (whole padded sequences)
+ * All sequences are stored once in device memory, back to back; one launch produces a batch from a
+ * row table.  A row is 4 x int32 (sequence, first frame, end frame, flip) -- the reference's
+ * `pairs` tuple (generators.py:39-48); `first_offset` is added to the first frame (2-D input:
+ * -(pad + causal_shift), generators.py:103-104; 3-D target: 0).  Frames outside the sequence
+ * replicate the nearest edge frame (np.pad 'edge', :108-118); flip negates feature 0 and reads
+ * joint j from src_joint[j] (:120-123, :137-143).  Results are exact copies (bit-exact). */
+typedef struct vp3d_gather_desc {
+  const float* src;         /* [total_frames][joints][features] fp32 */
+  const int64_t* seq_first; /* [n_seq] index of each sequence's first frame in src */
+  const int32_t* seq_len;   /* [n_seq] frames per sequence (>= 1) */
+  const int32_t* rows;      /* [n_windows][4] */
+  const int32_t* src_joint; /* [joints] mirror source of each joint, or NULL (no joint swap) */
+  float* out;               /* [n_windows][frames][joints][features] fp32 */
+  int32_t n_windows;
+  int32_t frames;           /* frames per window */
+  int32_t joints;
+  int32_t features;
+  int32_t first_offset;
+} vp3d_gather_desc;
+
+int vp3d_gather_windows(const vp3d_gather_desc* d, void* stream);
+
+/* Camera intrinsics rows for a batch: out[w] = cams[rows[w].sequence], entries 2 and 7 negated for
+ * flipped rows (generators.py:146-152).  cams: [n_seq][cam_dim] fp32. */
+int vp3d_gather_cameras(const float* cams, int32_t cam_dim, const int32_t* rows, int32_t n_windows,
+                        float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

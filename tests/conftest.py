@@ -18,7 +18,41 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Model fixtures (tests/golden/make_golden.py)."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if not n.startswith("gen_")]
+
+
+def generator_golden_names():
+    """Generator fixtures (tests/golden/make_generator_golden.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "gen_*.npz")))
+
+
+def load_generator_golden(name):
+    """Return (cfg, cameras|None, poses_3d|None, poses_2d, batches) where batches is a list of
+    (cam|None, b3|None, b2) float32 arrays exactly as the reference generator yielded them."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = json.loads(str(z["config"]))
+    n = len(cfg["lengths"])
+    p2 = [z[f"p2_{i}"] for i in range(n)]
+    p3 = [z[f"p3_{i}"] for i in range(n)] if cfg["use_3d"] else None
+    cams = list(z["cams"]) if cfg["use_cam"] else None
+    batches = []
+    for i in range(int(z["n_batches"])):
+        batches.append((z[f"cam_{i}"] if f"cam_{i}" in z.files else None,
+                        z[f"b3_{i}"] if f"b3_{i}" in z.files else None, z[f"b2_{i}"]))
+    return cfg, cams, p3, p2, batches
+
+
+def generator_kwargs(cfg):
+    """Constructor keywords shared by the reference generators, the oracle and the device classes."""
+    kw = dict(pad=cfg["pad"], causal_shift=cfg["causal_shift"], augment=cfg["augment"],
+              kps_left=cfg["left"], kps_right=cfg["right"], joints_left=cfg["left"],
+              joints_right=cfg["right"])
+    if cfg["kind"] == "chunked":
+        kw.update(shuffle=cfg["shuffle"], random_seed=cfg["random_seed"],
+                  endless=cfg.get("endless", False))
+    return kw
 
 
 def load_golden(name):

@@ -60,6 +60,24 @@ def test_plan_create_reports_errors_without_gpu():
         assert st == -3  # VP3D_ERR_CUDA: reported, not a crash and not a CPU fallback
 
 
+def test_gather_entry_points_report_errors_without_gpu():
+    """vp3d_gather_windows / vp3d_gather_cameras validate their arguments before any launch."""
+    ct = _capi.ctypes
+    lib = _capi.load()
+    assert ct.sizeof(_capi.GatherDesc) == 6 * 8 + 5 * 4 + 4  # 6 pointers, 5 int32, tail padding
+    assert lib.vp3d_gather_windows(None, None) == -1
+    d = _capi.GatherDesc()
+    d.n_windows, d.frames, d.joints, d.features = 1, 1, 100, 3  # 300 elements per frame > 256
+    assert lib.vp3d_gather_windows(ct.byref(d), None) == -2
+    d.joints = 17
+    assert lib.vp3d_gather_windows(ct.byref(d), None) == -1   # null pointers
+    assert b"null pointer" in lib.vp3d_last_error()
+    d.n_windows = 0
+    assert lib.vp3d_gather_windows(ct.byref(d), None) == 0    # empty batch: no-op, no launch
+    assert lib.vp3d_gather_cameras(None, 9, None, 0, None, None) == 0
+    assert lib.vp3d_gather_cameras(None, 9, None, 3, None, None) == -1
+
+
 @pytest.mark.parametrize("cls,kw", [
     (vp.TemporalModel, dict(filter_widths=[3, 3, 3], causal=False)),
     (vp.TemporalModel, dict(filter_widths=[3, 5, 3], causal=True, channels=128)),

@@ -64,6 +64,23 @@ class Grads(ctypes.Structure):
     ]
 
 
+class GatherDesc(ctypes.Structure):
+    """vp3d_gather_desc (include/vp3d_b200.h)."""
+    _fields_ = [
+        ("src", ctypes.c_void_p),
+        ("seq_first", ctypes.c_void_p),
+        ("seq_len", ctypes.c_void_p),
+        ("rows", ctypes.c_void_p),
+        ("src_joint", ctypes.c_void_p),
+        ("out", ctypes.c_void_p),
+        ("n_windows", ctypes.c_int32),
+        ("frames", ctypes.c_int32),
+        ("joints", ctypes.c_int32),
+        ("features", ctypes.c_int32),
+        ("first_offset", ctypes.c_int32),
+    ]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [
         ("a", ctypes.c_void_p),
@@ -152,6 +169,9 @@ SIGNATURES = {
     "vp3d_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
                                          ctypes.POINTER(ctypes.c_int)]),
     "vp3d_conv_gemm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_void_p]),
+    "vp3d_gather_windows": (ctypes.c_int, [ctypes.POINTER(GatherDesc), ctypes.c_void_p]),
+    "vp3d_gather_cameras": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None
