@@ -504,34 +504,55 @@ def run_input_pipeline(args):
     torch.cuda.synchronize()
     cpu_fed_ms = (time.perf_counter() - t0) / cpu_batches * 1e3
 
-    # training step (Optimized1f, fwd + bwd + Adam/amsgrad) fed by either pipeline
-    model = vp.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, channels=C).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True)
+    # training step (Optimized1f, fwd + bwd + AMSGrad) fed by either pipeline.  "stock" = the
+    # reference's torch.optim.Adam + torch loss expression (run.py:252, 413); "fused" = this
+    # repo's single-launch FusedAdam + fused mpjpe (rows f4, f2).
+    from videopose3d_b200 import loss as vloss
+    from videopose3d_b200.optim import FusedAdam
 
-    def step(x, y):
-        opt.zero_grad()
-        loss = torch.mean(torch.norm(model(x) - y, dim=-1))
-        loss.backward()
-        opt.step()
-        return loss
+    def make(kind):
+        torch.manual_seed(0)
+        m = vp.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, channels=C).to(dev).train()
+        if kind == "fused":
+            opt = FusedAdam(m.parameters(), lr=1e-3, amsgrad=True)
+            crit = vloss.mpjpe
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
+            crit = lambda p, y: torch.mean(torch.norm(p - y, dim=-1))  # noqa: E731
 
-    for _ in range(3):
-        _, y, x = next(it)
-        step(x, y)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, y, x = next(it)
-        loss = step(x, y)
-    loss.item()
-    torch.cuda.synchronize()
-    train_dev_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        def step(x, y):
+            opt.zero_grad()
+            loss = crit(m(x), y)
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    def timed_device_fed(step):
+        for _ in range(3):
+            _, y, x = next(it)
+            step(x, y)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(args.steps):
+            _, y, x = next(it)
+            loss = step(x, y)
+        b.record()
+        loss.item()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / args.steps * 1e3, a.elapsed_time(b) / args.steps
+
+    step_stock, step_fused = make("stock"), make("fused")
+    train_dev_ms, train_dev_gpu_ms = timed_device_fed(step_stock)
+    train_fused_ms, train_fused_gpu_ms = timed_device_fed(step_fused)
     host_steps = 4
     t0 = time.perf_counter()
     for _ in range(host_steps):
         _, b3, b2 = next(oit)
-        loss = step(torch.from_numpy(b2.astype("float32")).cuda(),
-                    torch.from_numpy(b3.astype("float32")).cuda())
+        loss = step_stock(torch.from_numpy(b2.astype("float32")).cuda(),
+                          torch.from_numpy(b3.astype("float32")).cuda())
     loss.item()
     torch.cuda.synchronize()
     train_host_ms = (time.perf_counter() - t0) / host_steps * 1e3
@@ -553,10 +574,15 @@ def run_input_pipeline(args):
                          "kind": "port", "cores": 1,
                          "sample": f"{cpu_batches} batches, oracle ChunkedGeneratorOracle (NumPy, single "
                                    "thread like the reference's Python loop) + astype(float32) + .cuda()"},
-        "train_step_fed_by_device_generator_ms": train_dev_ms,
-        "train_step_fed_by_host_generator_ms": train_host_ms,
-        "train_frames_per_s_device_fed": N_PER_GPU / (train_dev_ms * 1e-3),
-        "train_frames_per_s_host_fed": N_PER_GPU / (train_host_ms * 1e-3),
+        "train_step_ms": {
+            "host_generator+stock_adam (reference pipeline, CPU port)": train_host_ms,
+            "device_generator+stock_adam": train_dev_ms,
+            "device_generator+fused_adam+fused_mpjpe": train_fused_ms,
+            "device_generator+stock_adam (GPU time, events)": train_dev_gpu_ms,
+            "device_generator+fused_adam+fused_mpjpe (GPU time, events)": train_fused_gpu_ms},
+        "train_frames_per_s": {"host_fed": N_PER_GPU / (train_host_ms * 1e-3),
+                               "device_fed_stock": N_PER_GPU / (train_dev_ms * 1e-3),
+                               "device_fed_fused": N_PER_GPU / (train_fused_ms * 1e-3)},
     }
     print(json.dumps(line), flush=True)
     return line

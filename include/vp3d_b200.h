@@ -270,6 +270,33 @@ int vp3d_gather_windows(const vp3d_gather_desc* d, void* stream);
 int vp3d_gather_cameras(const float* cams, int32_t cam_dim, const int32_t* rows, int32_t n_windows,
                         float* out, void* stream);
 
+/* ---- training-step companions -------------------------------------------
+ * vp3d_adam_step: one launch of Adam / AMSGrad over a list of fp32 tensors -- what
+ * `optim.Adam(model.parameters(), lr=lr, amsgrad=True).step()` does per step (run.py:252, 264, 396,
+ * 420) with torch's update rule: g += weight_decay*p; m += (1-b1)(g-m); v = b2 v + (1-b2) g^2;
+ * vmax = max(vmax, v); p -= lr/(1-b1^t) * m / (sqrt(vmax)/sqrt(1-b2^t) + eps).  All pointers are
+ * device pointers; `tensors` itself is a host array.  max_exp_avg_sq == NULL selects plain Adam for
+ * that tensor.  `step` is the 1-based step count AFTER this update (torch's state['step']). */
+#define VP3D_ADAM_MAX_TENSORS 64 /* per launch; longer lists are split */
+typedef struct vp3d_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* max_exp_avg_sq; /* NULL = no AMSGrad */
+  int64_t numel;
+} vp3d_adam_tensor;
+
+int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, void* stream);
+
+/* Mean per-joint position error and its gradient in one launch (common/loss.py:11-17 mpjpe, :19-25
+ * weighted_mpjpe; used at run.py:359, 413): loss = mean_j w_j * ||pred_j - target_j||_2 over
+ * `joints_total` vectors of `dims` components; dpred (same shape as pred, may be NULL) receives
+ * d loss / d pred.  joint_w: per-vector weights or NULL (= 1).  loss: one device float. */
+int vp3d_mpjpe_fwd_bwd(const float* pred, const float* target, const float* joint_w,
+                       int64_t joints_total, int32_t dims, float* loss, float* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,50 @@ def test_gather_entry_points_report_errors_without_gpu():
     assert lib.vp3d_gather_cameras(None, 9, None, 3, None, None) == -1
 
 
+def test_step_op_entry_points_report_errors_without_gpu():
+    ct = _capi.ctypes
+    lib = _capi.load()
+    assert ct.sizeof(_capi.AdamTensor) == 48
+    assert lib.vp3d_adam_step(None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == 0  # nothing to do
+    assert lib.vp3d_adam_step(None, 2, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
+    row = (_capi.AdamTensor * 1)()
+    row[0].numel = 10
+    assert lib.vp3d_adam_step(row, 1, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
+    assert b"step must be >= 1" in lib.vp3d_last_error()
+    assert lib.vp3d_adam_step(row, 1, 1, 1e-3, 1.0, 0.999, 1e-8, 0.0, None) == -1  # beta1 = 1
+    assert lib.vp3d_adam_step(row, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1  # null pointers
+    assert b"null pointer" in lib.vp3d_last_error()
+    assert lib.vp3d_mpjpe_fwd_bwd(None, None, None, 4, 3, None, None, None) == -1
+    assert lib.vp3d_mpjpe_fwd_bwd(None, None, None, 4, 0, None, None, None) == -1
+
+
+def test_fused_adam_contract_without_gpu():
+    """Same state_dict layout as torch.optim.Adam (checkpoints interchange, run.py:600-608);
+    CPU tensors are refused rather than routed through torch."""
+    from videopose3d_b200.optim import FusedAdam
+    ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    ref = torch.optim.Adam(ps, lr=2e-3, amsgrad=True)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    ours = FusedAdam(ps, lr=1e-3, amsgrad=True)
+    ours.load_state_dict(ref.state_dict())
+    assert ours.param_groups[0]["lr"] == 2e-3 and ours.param_groups[0]["amsgrad"] is True
+    for p in ps:
+        assert set(ours.state[p]) == {"step", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"}
+        assert float(ours.state[p]["step"]) == 1.0
+    back = torch.optim.Adam(ps, lr=1e-3, amsgrad=True)
+    back.load_state_dict(ours.state_dict())
+    assert torch.equal(back.state[ps[0]]["exp_avg"], ref.state[ps[0]]["exp_avg"])
+    with pytest.raises(RuntimeError, match="CUDA float32"):
+        ours.step()
+    with pytest.raises(ValueError):
+        FusedAdam(ps, lr=-1.0)
+    from videopose3d_b200 import loss as vloss
+    with pytest.raises(RuntimeError, match="CUDA float32"):
+        vloss.mpjpe(torch.zeros(2, 1, 17, 3), torch.zeros(2, 1, 17, 3))
+
+
 @pytest.mark.parametrize("cls,kw", [
     (vp.TemporalModel, dict(filter_widths=[3, 3, 3], causal=False)),
     (vp.TemporalModel, dict(filter_widths=[3, 5, 3], causal=True, channels=128)),

@@ -1,0 +1,136 @@
+"""GPU: the training-step companions against plain PyTorch fp32:
+FusedAdam (vp3d_adam_step) vs torch.optim.Adam, fused mpjpe / weighted_mpjpe (vp3d_mpjpe_fwd_bwd)
+vs the reference formulas of common/loss.py:11-25.  Floating point: tolerances stated per test."""
+import numpy as np
+import pytest
+import torch
+
+import videopose3d_b200 as vp
+from videopose3d_b200 import loss as vloss
+from videopose3d_b200.optim import FusedAdam
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(dev, seed, n_extra=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(1024, 34, 3), (257,), (8193,), (3, 5, 7), (1,), (64, 64, 1), (16385,)] + [(33,)] * n_extra
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    # an unaligned (4-byte aligned only) parameter carved out of a larger buffer
+    buf = torch.randn(1003, generator=g).to(dev)
+    ps.append(torch.nn.Parameter(buf[1:1000]))
+    return ps
+
+
+def _close(a, b, rtol, atol):
+    return torch.allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("amsgrad,weight_decay,n_extra", [(True, 0.0, 0), (False, 0.0, 0),
+                                                          (True, 0.01, 70)])
+def test_fused_adam_matches_torch(cuda_device, amsgrad, weight_decay, n_extra):
+    """8 steps with fresh random gradients and an lr decay in between (run.py:583-586).
+    Tolerances (fp32 round-off of a different operation order): parameters 2e-6 relative + 2e-7
+    absolute (one Adam step moves a parameter by ~lr = 1e-3); first moment 2e-6 + 2e-6 absolute
+    (it crosses zero, gradients are O(1..8)); second moments 5e-6 relative."""
+    ours_p = _params(cuda_device, 1, n_extra)
+    ref_p = [torch.nn.Parameter(p.detach().clone()) for p in ours_p]
+    kw = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay, amsgrad=amsgrad)
+    ours, ref = FusedAdam(ours_p, **kw), torch.optim.Adam(ref_p, **kw)
+    g = torch.Generator().manual_seed(2)
+    for step in range(8):
+        for a, b in zip(ours_p, ref_p):
+            grad = (torch.randn(a.shape, generator=g) * (0.1 + step)).to(cuda_device)
+            a.grad, b.grad = grad.clone(), grad.clone()
+        v0 = ours_p[0]._version
+        ours.step()
+        ref.step()
+        assert ours_p[0]._version > v0  # the weight-pack cache keys on the version counter
+        if step == 3:
+            for opt in (ours, ref):
+                for group in opt.param_groups:
+                    group["lr"] *= 0.95
+    for a, b in zip(ours_p, ref_p):
+        assert _close(a, b, 2e-6, 2e-7)
+        assert _close(ours.state[a]["exp_avg"], ref.state[b]["exp_avg"], 2e-6, 2e-6)
+        for key in ("exp_avg_sq",) + (("max_exp_avg_sq",) if amsgrad else ()):
+            assert _close(ours.state[a][key], ref.state[b][key], 5e-6, 1e-9), key
+        assert float(ours.state[a]["step"]) == float(ref.state[b]["step"]) == 8.0
+
+
+def test_fused_adam_checkpoint_round_trip(cuda_device):
+    ours_p = _params(cuda_device, 3)
+    ref_p = [torch.nn.Parameter(p.detach().clone()) for p in ours_p]
+    ours, ref = FusedAdam(ours_p, lr=1e-3, amsgrad=True), torch.optim.Adam(ref_p, lr=1e-3, amsgrad=True)
+    g = torch.Generator().manual_seed(4)
+
+    def grads():
+        for a, b in zip(ours_p, ref_p):
+            grad = torch.randn(a.shape, generator=g).to(cuda_device)
+            a.grad, b.grad = grad.clone(), grad.clone()
+    grads(); ours.step(); ref.step()
+    # swap optimiser states through state_dict() and continue
+    sd_ours, sd_ref = ours.state_dict(), ref.state_dict()
+    ours.load_state_dict(sd_ref)
+    ref.load_state_dict(sd_ours)
+    grads(); ours.step(); ref.step()
+    for a, b in zip(ours_p, ref_p):
+        assert _close(a, b, 2e-6, 2e-7)
+
+
+def test_training_with_fused_adam_tracks_torch_adam(cuda_device):
+    """Optimized1f, fp32-faithful GEMMs, dropout 0: five optimiser steps from the same start with
+    either optimiser give the same loss curve (<= 1e-4 relative) and parameters (<= 1e-4 of scale)."""
+    torch.manual_seed(0)
+    a = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
+    b = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
+    b.load_state_dict(a.state_dict())
+    a, b = a.to(cuda_device).train(), b.to(cuda_device).train()
+    a.set_train_precision("bf16x3"); b.set_train_precision("bf16x3")
+    oa = FusedAdam(a.parameters(), lr=1e-3, amsgrad=True)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-3, amsgrad=True)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(5):
+        x = (torch.rand(64, 27, 17, 2, generator=g) * 2 - 1).to(cuda_device)
+        y = (torch.randn(64, 1, 17, 3, generator=g) * 0.3).to(cuda_device)
+        oa.zero_grad(); ob.zero_grad()
+        la = vloss.mpjpe(a(x), y)
+        lb = torch.mean(torch.norm(b(x) - y, dim=-1))
+        la.backward(); lb.backward()
+        oa.step(); ob.step()
+        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(lb))
+    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        scale = float(pb.abs().max()) + 1e-12
+        assert float((pa - pb).abs().max()) <= 1e-4 * scale + 2e-6, na
+
+
+def test_mpjpe_matches_reference_formula(cuda_device):
+    g = torch.Generator().manual_seed(5)
+    pred = (torch.randn(1024, 1, 17, 3, generator=g) * 0.5).to(cuda_device).requires_grad_(True)
+    tgt = (torch.randn(1024, 1, 17, 3, generator=g) * 0.5).to(cuda_device)
+    with torch.no_grad():
+        tgt[3, 0, 5] = pred[3, 0, 5]  # a zero-length error vector: gradient must be 0, not NaN
+    ref_in = pred.detach().clone().requires_grad_(True)
+    ref = torch.mean(torch.norm(ref_in - tgt, dim=len(tgt.shape) - 1))   # loss.py:17
+    ref.backward()
+    ours = vloss.mpjpe(pred, tgt)
+    (ours * 3.0).backward()
+    assert ours.shape == () and abs(float(ours) - float(ref)) <= 2e-6 * float(ref)
+    assert torch.isfinite(pred.grad).all() and float(pred.grad[3, 0, 5].abs().max()) == 0.0
+    assert _close(pred.grad, 3.0 * ref_in.grad, 1e-5, 1e-10)
+    with torch.no_grad():  # evaluation use (run.py:452): no gradient buffer, same value
+        assert abs(float(vloss.mpjpe(pred, tgt)) - float(ref)) <= 2e-6 * float(ref)
+
+
+def test_weighted_mpjpe_matches_reference_formula(cuda_device):
+    g = torch.Generator().manual_seed(6)
+    pred = (torch.randn(512, 1, 1, 3, generator=g)).to(cuda_device).requires_grad_(True)
+    tgt = (torch.randn(512, 1, 1, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])).to(cuda_device)
+    w = 1 / tgt[:, :, :, 2]                                   # run.py:358
+    ref_in = pred.detach().clone().requires_grad_(True)
+    ref = torch.mean(w * torch.norm(ref_in - tgt, dim=len(tgt.shape) - 1))  # loss.py:25
+    ref.backward()
+    ours = vloss.weighted_mpjpe(pred, tgt, w)
+    ours.backward()
+    assert abs(float(ours) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert _close(pred.grad, ref_in.grad, 1e-5, 1e-10)

@@ -64,6 +64,18 @@ class Grads(ctypes.Structure):
     ]
 
 
+class AdamTensor(ctypes.Structure):
+    """vp3d_adam_tensor (include/vp3d_b200.h)."""
+    _fields_ = [
+        ("param", ctypes.c_void_p),
+        ("grad", ctypes.c_void_p),
+        ("exp_avg", ctypes.c_void_p),
+        ("exp_avg_sq", ctypes.c_void_p),
+        ("max_exp_avg_sq", ctypes.c_void_p),
+        ("numel", ctypes.c_int64),
+    ]
+
+
 class GatherDesc(ctypes.Structure):
     """vp3d_gather_desc (include/vp3d_b200.h)."""
     _fields_ = [
@@ -172,6 +184,12 @@ SIGNATURES = {
     "vp3d_gather_windows": (ctypes.c_int, [ctypes.POINTER(GatherDesc), ctypes.c_void_p]),
     "vp3d_gather_cameras": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "vp3d_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamTensor), ctypes.c_int32, ctypes.c_int64,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p]),
+    "vp3d_mpjpe_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,198 @@
+// Training-step companions of the model.
+//
+//  * vp3d_adam_step: AMSGrad/Adam over every parameter tensor in ONE launch.  Reference:
+//    `optim.Adam(model.parameters(), lr=lr, amsgrad=True)` + `optimizer.step()` (run.py:252, 264,
+//    396, 420), lr decay by mutating param_groups (run.py:583-586).  torch runs 8 multi-tensor
+//    launches over 16.95 M parameters; this is one HBM-bound pass: 20 B read + 16 B written per
+//    element.
+//  * vp3d_mpjpe_fwd_bwd: mean per-joint position error (loss.py:11-17, run.py:413-418) and its
+//    gradient w.r.t. the prediction in one launch.
+#include "internal.cuh"
+
+namespace vp3d {
+namespace {
+
+constexpr int kAdamThreads = 256;
+constexpr int kAdamChunk = 8192;  // elements per block
+
+struct AdamBatch {
+  vp3d_adam_tensor t[VP3D_ADAM_MAX_TENSORS];
+  int first_block[VP3D_ADAM_MAX_TENSORS + 1];
+  int n;
+};
+
+struct AdamHyper {
+  float one_minus_beta1, beta2, one_minus_beta2, eps, weight_decay, step_size, bc2_sqrt;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float& vmax,
+                                            bool amsgrad, const AdamHyper& h) {
+  if (h.weight_decay != 0.0f) g = fmaf(h.weight_decay, p, g);
+  m = m + h.one_minus_beta1 * (g - m);
+  v = v * h.beta2 + (h.one_minus_beta2 * g) * g;
+  float second = v;
+  if (amsgrad) {
+    vmax = fmaxf(vmax, v);
+    second = vmax;
+  }
+  const float denom = sqrtf(second) / h.bc2_sqrt + h.eps;
+  p = p - h.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(kAdamThreads)
+adam_step_kernel(const __grid_constant__ AdamBatch batch, const AdamHyper h) {
+  // which tensor owns this block (<= 64 entries: a short scan)
+  int ti = 0;
+  while (ti + 1 < batch.n && (int)blockIdx.x >= batch.first_block[ti + 1]) ++ti;
+  const vp3d_adam_tensor& t = batch.t[ti];
+  const long long begin = (long long)(blockIdx.x - batch.first_block[ti]) * kAdamChunk;
+  const long long end = min(begin + (long long)kAdamChunk, (long long)t.numel);
+  const bool amsgrad = t.max_exp_avg_sq != nullptr;
+  const uintptr_t bits = (uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg |
+                         (uintptr_t)t.exp_avg_sq | (uintptr_t)t.max_exp_avg_sq;
+  long long i = begin;
+  if ((bits & 15) == 0) {  // all five streams 16-byte aligned (chunks are multiples of 4 elements)
+    const long long vec_end = begin + ((end - begin) & ~3ll);
+    for (long long k = begin + 4ll * threadIdx.x; k < vec_end; k += 4ll * kAdamThreads) {
+      float4 p = *reinterpret_cast<float4*>(t.param + k);
+      const float4 g = *reinterpret_cast<const float4*>(t.grad + k);
+      float4 m = *reinterpret_cast<float4*>(t.exp_avg + k);
+      float4 v = *reinterpret_cast<float4*>(t.exp_avg_sq + k);
+      float4 x = amsgrad ? *reinterpret_cast<float4*>(t.max_exp_avg_sq + k) : make_float4(0, 0, 0, 0);
+      adam_update(p.x, g.x, m.x, v.x, x.x, amsgrad, h);
+      adam_update(p.y, g.y, m.y, v.y, x.y, amsgrad, h);
+      adam_update(p.z, g.z, m.z, v.z, x.z, amsgrad, h);
+      adam_update(p.w, g.w, m.w, v.w, x.w, amsgrad, h);
+      *reinterpret_cast<float4*>(t.param + k) = p;
+      *reinterpret_cast<float4*>(t.exp_avg + k) = m;
+      *reinterpret_cast<float4*>(t.exp_avg_sq + k) = v;
+      if (amsgrad) *reinterpret_cast<float4*>(t.max_exp_avg_sq + k) = x;
+    }
+    i = vec_end;
+  }
+  for (long long k = i + threadIdx.x; k < end; k += kAdamThreads) {
+    float p = t.param[k], m = t.exp_avg[k], v = t.exp_avg_sq[k];
+    float x = amsgrad ? t.max_exp_avg_sq[k] : 0.0f;
+    adam_update(p, t.grad[k], m, v, x, amsgrad, h);
+    t.param[k] = p;
+    t.exp_avg[k] = m;
+    t.exp_avg_sq[k] = v;
+    if (amsgrad) t.max_exp_avg_sq[k] = x;
+  }
+}
+
+// ---- MPJPE ------------------------------------------------------------------------------------
+
+constexpr int kLossThreads = 256;
+
+// One thread per joint: d = ||pred - target||_2 over the last axis (dims = 3 for poses);
+// loss += weight * w_j * d, dpred = weight * w_j * (pred - target) / d  (0 where d == 0, as
+// autograd's norm backward yields for a zero vector).  weight = 1 / joints_total folds the mean;
+// w_j = 1 without per-joint weights (mpjpe) or the caller's weight (weighted_mpjpe).
+__global__ void __launch_bounds__(kLossThreads)
+mpjpe_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+             const float* __restrict__ joint_w, float* __restrict__ dpred, float* __restrict__ loss,
+             long long joints_total, int dims, float weight) {
+  __shared__ float s_part[kLossThreads / 32];
+  const long long j = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  float d = 0.0f;
+  if (j < joints_total) {
+    const float* p = pred + j * dims;
+    const float* q = target + j * dims;
+    float sq = 0.0f;
+    for (int k = 0; k < dims; ++k) {
+      const float e = p[k] - q[k];
+      sq = fmaf(e, e, sq);
+    }
+    d = sqrtf(sq);
+    const float wj = joint_w != nullptr ? joint_w[j] : 1.0f;
+    if (dpred != nullptr) {
+      const float s = d > 0.0f ? weight * wj / d : 0.0f;
+      for (int k = 0; k < dims; ++k) dpred[j * dims + k] = (p[k] - q[k]) * s;
+    }
+    d *= wj;
+  }
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kLossThreads / 32 ? s_part[threadIdx.x] : 0.0f;
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss, v * weight);
+  }
+}
+
+}  // namespace
+}  // namespace vp3d
+
+#define VP3D_EXPORT extern "C" __attribute__((visibility("default")))
+
+VP3D_EXPORT int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step,
+                               double lr, double beta1, double beta2, double eps,
+                               double weight_decay, void* stream) {
+  using namespace vp3d;
+  if (n_tensors < 0 || (n_tensors > 0 && tensors == nullptr))
+    return fail(VP3D_ERR_INVALID, "vp3d_adam_step: bad tensor list");
+  if (step < 1) return fail(VP3D_ERR_INVALID, "vp3d_adam_step: step must be >= 1 (got %lld)",
+                            (long long)step);
+  if (!(lr >= 0.0) || !(eps >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) ||
+      !(beta2 >= 0.0 && beta2 < 1.0) || !(weight_decay >= 0.0))
+    return fail(VP3D_ERR_INVALID, "vp3d_adam_step: invalid hyper-parameter (lr %g, betas %g %g, "
+                "eps %g, weight_decay %g)", lr, beta1, beta2, eps, weight_decay);
+  // bias corrections in double on the host, as torch.optim.Adam computes them from python floats
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamHyper h;
+  h.one_minus_beta1 = (float)(1.0 - beta1);
+  h.beta2 = (float)beta2;
+  h.one_minus_beta2 = (float)(1.0 - beta2);
+  h.eps = (float)eps;
+  h.weight_decay = (float)weight_decay;
+  h.step_size = (float)(lr / bc1);
+  h.bc2_sqrt = (float)sqrt(bc2);
+  for (int base = 0; base < n_tensors; base += VP3D_ADAM_MAX_TENSORS) {
+    AdamBatch b;
+    b.n = 0;
+    int blocks = 0;
+    const int stop = base + VP3D_ADAM_MAX_TENSORS < n_tensors ? base + VP3D_ADAM_MAX_TENSORS : n_tensors;
+    for (int i = base; i < stop; ++i) {
+      const vp3d_adam_tensor& t = tensors[i];
+      if (t.numel < 0) return fail(VP3D_ERR_INVALID, "vp3d_adam_step: tensor %d has numel < 0", i);
+      if (t.numel == 0) continue;
+      if (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq)
+        return fail(VP3D_ERR_INVALID, "vp3d_adam_step: tensor %d has a null pointer", i);
+      const long long nb = (t.numel + kAdamChunk - 1) / kAdamChunk;
+      if (blocks + nb > 0x3fffffff)
+        return fail(VP3D_ERR_UNSUPPORTED, "vp3d_adam_step: too many elements in one launch");
+      b.t[b.n] = t;
+      b.first_block[b.n] = blocks;
+      blocks += (int)nb;
+      ++b.n;
+    }
+    b.first_block[b.n] = blocks;
+    if (blocks == 0) continue;
+    adam_step_kernel<<<blocks, kAdamThreads, 0, (cudaStream_t)stream>>>(b, h);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return VP3D_OK;
+}
+
+VP3D_EXPORT int vp3d_mpjpe_fwd_bwd(const float* pred, const float* target, const float* joint_w,
+                                   int64_t joints_total, int32_t dims, float* loss, float* dpred,
+                                   void* stream) {
+  using namespace vp3d;
+  if (joints_total < 0 || dims < 1 || dims > 16)
+    return fail(VP3D_ERR_INVALID, "vp3d_mpjpe_fwd_bwd: bad sizes (joints %lld, dims %d)",
+                (long long)joints_total, dims);
+  if (loss == nullptr) return fail(VP3D_ERR_INVALID, "vp3d_mpjpe_fwd_bwd: null loss pointer");
+  if (joints_total > 0 && (pred == nullptr || target == nullptr))
+    return fail(VP3D_ERR_INVALID, "vp3d_mpjpe_fwd_bwd: null pointer");
+  CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  if (joints_total == 0) return VP3D_OK;
+  const long long blocks = (joints_total + kLossThreads - 1) / kLossThreads;
+  if (blocks > 0x7fffffffll) return fail(VP3D_ERR_UNSUPPORTED, "vp3d_mpjpe_fwd_bwd: too large");
+  mpjpe_kernel<<<(unsigned)blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
+      pred, target, joint_w, dpred, loss, joints_total, dims, (float)(1.0 / (double)joints_total));
+  CUDA_TRY(cudaGetLastError());
+  return VP3D_OK;
+}
