@@ -96,7 +96,7 @@ def test_step_op_entry_points_report_errors_without_gpu():
 
 
 def test_fused_adam_contract_without_gpu():
-    """Same state_dict layout as torch.optim.Adam (checkpoints interchange, run.py:600-608);
+    """Same state_dict layout as torch.optim.Adam (checkpoints interchange, run.py:295-296, 600-608);
     CPU tensors are refused rather than routed through torch."""
     from videopose3d_b200.optim import FusedAdam
     ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]

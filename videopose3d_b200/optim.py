@@ -5,7 +5,7 @@ Drop-in for the optimiser the reference constructs with
 `optimizer.zero_grad()` / `optimizer.step()` (run.py:347, 396, 409, 420) and
 `param_group['lr'] *= lr_decay` (run.py:583-586): same constructor arguments, same update rule,
 same `state_dict()` layout (`step`, `exp_avg`, `exp_avg_sq`, `max_exp_avg_sq` per parameter), so
-checkpoints written by either optimiser load into the other (run.py:600-608, 303-304).
+checkpoints written by either optimiser load into the other (run.py:295-296, 600-608).
 
 `step()` hands every parameter of a group to `vp3d_adam_step` (csrc/step_ops.cu): one kernel launch
 reads p, g, m, v, vmax and writes p, m, v, vmax once (36 B per element) instead of the eight
