@@ -382,8 +382,8 @@ def run_ours(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)",
-                      "mixed": "bf16 (FLOP-dominant blocks plain bf16; expand/shrink/tail blocks "
-                               "split-bf16; fp32 accumulate)"}[args.precision],
+                      "mixed": "bf16 (residual blocks plain bf16 on a hi+lo residual stream; expand "
+                               "and shrink split-bf16; fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {
                 "workload": "TemporalModel arc=3,3,3,3,3 T=243 C=1024 J=17 eval forward, N=1024 "

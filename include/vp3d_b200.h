@@ -43,9 +43,9 @@ typedef enum {
 typedef enum {
   VP3D_PRECISION_BF16 = 0,   /* bf16 operands, fp32 accumulate (fast path; BASELINE cfg 2) */
   VP3D_PRECISION_BF16X3 = 1, /* split-bf16 (hi+lo) operands, 3 MMAs per product: fp32-faithful */
-  VP3D_PRECISION_MIXED = 2   /* eval default: bf16 on the FLOP-dominant blocks, split-bf16 on the
-                                cheap layers (expand, shrink, narrow tail blocks), residual stream
-                                kept in hi+lo planes; <= 1e-3 of fp32 at ~bf16 cost */
+  VP3D_PRECISION_MIXED = 2   /* eval default: bf16 residual blocks, split-bf16 expand and shrink
+                                (and blocks below 0.5% of the FLOPs), residual stream kept in
+                                hi+lo planes; ~1e-3 of fp32 (<= 2e-3) close to bf16 cost */
 } vp3d_precision;
 
 /* Constructor arguments of TemporalModel / TemporalModelOptimized1f (model.py:85-86, :151-152). */

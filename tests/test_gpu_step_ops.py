@@ -78,32 +78,45 @@ def test_fused_adam_checkpoint_round_trip(cuda_device):
         assert _close(a, b, 2e-6, 2e-7)
 
 
-def test_training_with_fused_adam_tracks_torch_adam(cuda_device):
-    """Optimized1f, fp32-faithful GEMMs, dropout 0: five optimiser steps from the same start with
-    either optimiser give the same loss curve (<= 1e-4 relative).  Parameters: Adam's m / sqrt(v)
-    normalisation turns run-to-run round-off in a small gradient (atomics order in the batch
-    statistics, a different loss kernel) into a visible fraction of lr, so the bound is stated in
-    units of the distance a parameter can travel: <= 5 % of steps * lr."""
+def test_fused_adam_drives_the_model(cuda_device):
+    """FusedAdam on the real model (gradients are views of the model's flat gradient buffer; the
+    weight packs are refreshed through the version counter): at every step a twin parameter set
+    receives the SAME gradients and is stepped by torch.optim.Adam -> parameters agree to fp32
+    round-off (2e-6 relative + 1e-6 absolute, lr = 1e-3); afterwards the trained model and a fresh
+    model loaded with the twin's parameters produce the same training-mode output (<= 2e-5), which
+    only holds if the kernels really run on the updated weights."""
     torch.manual_seed(0)
-    a = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
-    b = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=[3, 3, 3], dropout=0.0, channels=128)
-    b.load_state_dict(a.state_dict())
-    a, b = a.to(cuda_device).train(), b.to(cuda_device).train()
-    a.set_train_precision("bf16x3"); b.set_train_precision("bf16x3")
+    kw = dict(filter_widths=[3, 3, 3], dropout=0.0, channels=128)
+    a = vp.TemporalModelOptimized1f(17, 2, 17, **kw).to(cuda_device).train()
+    a.set_train_precision("bf16x3")
+    twin = [torch.nn.Parameter(p.detach().clone()) for p in a.parameters()]
     oa = FusedAdam(a.parameters(), lr=1e-3, amsgrad=True)
-    ob = torch.optim.Adam(b.parameters(), lr=1e-3, amsgrad=True)
+    ob = torch.optim.Adam(twin, lr=1e-3, amsgrad=True)
     g = torch.Generator().manual_seed(1)
+    losses = []
     for _ in range(5):
         x = (torch.rand(64, 27, 17, 2, generator=g) * 2 - 1).to(cuda_device)
         y = (torch.randn(64, 1, 17, 3, generator=g) * 0.3).to(cuda_device)
-        oa.zero_grad(); ob.zero_grad()
-        la = vloss.mpjpe(a(x), y)
-        lb = torch.mean(torch.norm(b(x) - y, dim=-1))
-        la.backward(); lb.backward()
-        oa.step(); ob.step()
-        assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item())
-    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
-        assert float((pa - pb).abs().max()) <= 0.05 * 5 * 1e-3, na
+        oa.zero_grad()
+        loss = vloss.mpjpe(a(x), y)
+        loss.backward()
+        for pa, pb in zip(a.parameters(), twin):
+            pb.grad = pa.grad.detach().clone()
+        oa.step()
+        ob.step()
+        losses.append(loss.item())
+        for (name, pa), pb in zip(a.named_parameters(), twin):
+            assert _close(pa, pb, 2e-6, 1e-6), name
+    assert losses[-1] < losses[0]  # it trains
+    b = vp.TemporalModelOptimized1f(17, 2, 17, **kw)
+    b.load_state_dict(a.state_dict())
+    with torch.no_grad():
+        for pb, pt in zip(b.parameters(), twin):
+            pb.copy_(pt)
+    b = b.to(cuda_device).train()
+    b.set_train_precision("bf16x3")
+    ya, yb = a(x).detach(), b(x).detach()
+    assert float((ya - yb).abs().max()) <= 2e-5 * float(yb.abs().max())
 
 
 def test_mpjpe_matches_reference_formula(cuda_device):

@@ -573,9 +573,10 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   // Per-layer operand precision.  index 0 = expand, 1..nb = residual blocks, nb+1 = shrink.
   //   bf16   : every GEMM single-plane bf16.
   //   bf16x3 : every GEMM split-bf16 (3 MMAs per product).
-  //   mixed  : the residual stream X keeps hi+lo planes (skip path exact); GEMMs holding < 3% of
-  //            the forward FLOPs (expand, shrink, the narrow tail blocks) run split-bf16, the
-  //            FLOP-dominant blocks run plain bf16 on the hi plane.
+  //   mixed  : the residual stream X keeps hi+lo planes (skip path exact); expand and shrink run
+  //            split-bf16 (they carry most of the bf16 error: profiles/r1_precision_study.txt),
+  //            residual blocks run plain bf16 on the hi plane unless they hold < 0.5% of the
+  //            forward FLOPs (negligible even at the narrow-tile rate of such layers).
   bool x3[VP3D_MAX_WIDTHS + 1];
   {
     double fl[VP3D_MAX_WIDTHS + 1], total = 0.0;
@@ -586,7 +587,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     for (int i = 0; i <= p->nb + 1; ++i) {
       if (p->cfg.precision == VP3D_PRECISION_BF16) x3[i] = false;
       else if (p->cfg.precision == VP3D_PRECISION_BF16X3) x3[i] = true;
-      else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.03 * total);
+      else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.005 * total);
     }
   }
 

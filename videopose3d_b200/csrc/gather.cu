@@ -15,11 +15,11 @@ namespace vp3d {
 namespace {
 
 constexpr int kGatherThreads = 256;
-constexpr int kGatherFrames = 32;   // frames per block
+constexpr int kGatherFrames = 128;  // frames per block (amortises the per-block table set-up)
 constexpr int kMaxRowElems = 256;   // joints * features supported by the shared index table
 
 // div_magic = floor(2^32 / row_elems) + 1: floor(i / row_elems) == umulhi(i, div_magic) for every
-// i < 2^32 / row_elems, which covers a tile (i < kGatherFrames * kMaxRowElems = 2^13).
+// i < 2^32 / row_elems, which covers a tile (i < kGatherFrames * kMaxRowElems = 2^15).
 __global__ void __launch_bounds__(kGatherThreads)
 gather_windows_kernel(const float* __restrict__ src, const long long* __restrict__ seq_first,
                       const int* __restrict__ seq_len, const int* __restrict__ rows,

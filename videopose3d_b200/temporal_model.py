@@ -137,8 +137,8 @@ class TemporalModelBase(nn.Module):
 
     # ------------------------------------------------------------------ engine controls
     def set_precision(self, precision):
-        """'mixed' (default: bf16 on the FLOP-dominant blocks, split-bf16 on the cheap layers,
-        exact residual stream), 'bf16' (every GEMM plain bf16) or 'bf16x3' (every GEMM split-bf16,
+        """'mixed' (default: bf16 residual blocks, split-bf16 expand / shrink, exact residual
+        stream), 'bf16' (every GEMM plain bf16) or 'bf16x3' (every GEMM split-bf16,
         fp32-faithful).  Not in the reference."""
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
