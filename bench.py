@@ -477,8 +477,35 @@ def run_input_pipeline(args):
         b.record()
     torch.cuda.synchronize()
     gather_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    out_bytes = N_PER_GPU * (T * J * F + J * 3) * 4
-    algo_bytes = 2 * out_bytes              # every output element is read once and written once
+    # kernel-only time of the dominant gather (2-D windows): the C-ABI entry point called back to
+    # back on 8 rotating 33.8 MB outputs (working set > L2), CUDA events around the burst
+    import ctypes
+    from videopose3d_b200 import _capi
+    lib = _capi.load()
+    outs = [torch.empty((N_PER_GPU, T, J, F), dtype=torch.float32, device=dev) for _ in range(8)]
+    rows = gen._rows_dev
+    descs = []
+    for k in range(args.steps):
+        d = _capi.GatherDesc()
+        d.src, d.seq_first, d.seq_len = gen._p2.data.data_ptr(), gen._p2.seq_first.data_ptr(), gen._p2.seq_len.data_ptr()
+        d.rows = rows.data_ptr() + 16 * N_PER_GPU * (k % 64)
+        d.src_joint = gen._p2.src_joint.data_ptr()
+        d.out = outs[k % 8].data_ptr()
+        d.n_windows, d.frames, d.joints, d.features, d.first_offset = N_PER_GPU, T, J, F, -121
+        descs.append(d)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for d in descs[:8]:
+        _capi.check(lib.vp3d_gather_windows(ctypes.byref(d), stream), "vp3d_gather_windows")
+    torch.cuda.synchronize()
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ka.record()
+    for d in descs:
+        lib.vp3d_gather_windows(ctypes.byref(d), stream)
+    kb.record()
+    torch.cuda.synchronize()
+    kernel_ms = ka.elapsed_time(kb) / args.steps
+    win_bytes = N_PER_GPU * T * J * F * 4
+    algo_bytes = 2 * win_bytes              # every output element is read once and written once
     _, peak_gbs, peak_src = load_peaks()
     # host wall clock per batch of the device generator (Python + 2 launches, GPU idle otherwise)
     t0 = time.perf_counter()
@@ -563,13 +590,16 @@ def run_input_pipeline(args):
                                f"augmentation, {n_seq} sequences of 1000-6000 frames "
                                f"({int(lens.sum())} frames, {int(lens.sum()) * J * F * 4 / 1e6:.0f} MB of 2-D input)",
                    "l2": "256 MiB memset between timed gathers"},
-        "device_generator": {"gather_ms_per_batch": gather_ms, "host_wall_ms_per_batch": dev_wall_ms,
+        "device_generator": {"gather_ms_per_batch_incl_launch_gaps": gather_ms, "host_wall_ms_per_batch": dev_wall_ms,
                              "dataset_upload_s": upload_s, "epoch_start_s": epoch_start_s,
                              "h2d_bytes_per_step": 0, "gpu_launches_per_batch": 2},
-        "roofline": {"bound": "hbm", "achieved": algo_bytes / (gather_ms * 1e-3) / 1e9, "peak": peak_gbs,
-                     "unit": "GB/s", "frac": algo_bytes / (gather_ms * 1e-3) / 1e9 / peak_gbs,
-                     "algorithmic_bytes": algo_bytes, "traffic": None, "peak_source": peak_src,
-                     "kernel": "gather_windows_kernel (2-D windows) + (3-D targets)"},
+        "roofline": {"bound": "hbm", "achieved": algo_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peak_gbs,
+                     "unit": "GB/s", "frac": algo_bytes / (kernel_ms * 1e-3) / 1e9 / peak_gbs,
+                     "algorithmic_bytes": algo_bytes, "ms_per_launch": kernel_ms,
+                     "traffic": 39.4e6, "traffic_source": "ncu --set full dram read+write of this launch "
+                     "(profiles/r1n_ncu_full_gather.csv; most reads and part of the writes stay in L2)",
+                     "peak_source": peak_src,
+                     "kernel": "gather_windows_kernel, 2-D windows 1024 x (243,17,2) fp32"},
         "cpu_baseline": {"generator_ms_per_batch": cpu_gen_ms, "generator_cast_h2d_ms_per_batch": cpu_fed_ms,
                          "kind": "port", "cores": 1,
                          "sample": f"{cpu_batches} batches, oracle ChunkedGeneratorOracle (NumPy, single "
