@@ -123,6 +123,34 @@ def main():
         del ref
         torch.cuda.empty_cache()
 
+    if "seq" in what:
+        # the reference's inference use (UnchunkedGenerator + evaluate(), run.py:652-721): one whole
+        # video per forward, test-time flip augmentation -> batch of 2 sequences, every frame
+        # predicted.  This is the dilated schedule (no cone pruning possible).
+        frames = 6000
+        xs = (torch.rand(2, frames + 242, J, F, generator=g) * 2 - 1).to(dev)
+        m = vp.TemporalModel(J, F, J, filter_widths=ARC, channels=C).to(dev).eval()
+        for prec in ("mixed", "bf16", "bf16x3"):
+            m.set_precision(prec)
+            with torch.no_grad():
+                med, best = timeit(lambda: m(xs), args.iters)
+            emit(what="eval_sequence_2x6000", impl="vp3d_b200", precision=prec, ms_median=med,
+                 ms_best=best, frames_per_s=2 * frames / med * 1e3, launches=m.last_launch_count())
+        del m
+        ref = CudnnTemporal(strided=False).to(dev).eval()
+        for name, tf32, autocast in (("fp32_tf32", True, False), ("bf16_autocast", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def run_seq():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return ref(xs)
+            med, best = timeit(run_seq, max(5, args.iters // 3), warmup=3)
+            emit(what="eval_sequence_2x6000", impl="pytorch_cudnn_reference_arch", precision=name,
+                 ms_median=med, ms_best=best, frames_per_s=2 * frames / med * 1e3)
+        del ref
+        torch.cuda.empty_cache()
+
     if "train" in what:
         for prec in ("bf16", "bf16x3"):
             m = vp.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, channels=C).to(dev).train()
