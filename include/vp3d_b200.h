@@ -297,6 +297,16 @@ int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t s
 int vp3d_mpjpe_fwd_bwd(const float* pred, const float* target, const float* joint_w,
                        int64_t joints_total, int32_t dims, float* loss, float* dpred, void* stream);
 
+/* Re-projection loss of the semi-supervised branch and its gradients in one launch (run.py:374-379:
+ * `mpjpe(project_to_2d(predicted_pos + predicted_traj, cam), target_2d)`, projection per
+ * common/camera.py:37-67, or :69-88 when `linear` != 0).  pos: [samples][frames][joints][3],
+ * traj: [samples][frames][1][3], cam: [samples][9] = f(2) c(2) k(3) p(2), target:
+ * [samples][frames][joints][2]; dpos / dtraj (same shapes as pos / traj) are both NULL or both set. */
+int vp3d_projected_mpjpe_fwd_bwd(const float* pos, const float* traj, const float* cam,
+                                 const float* target, int64_t samples, int32_t frames_per_sample,
+                                 int32_t joints, int32_t linear, float* loss, float* dpos,
+                                 float* dtraj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

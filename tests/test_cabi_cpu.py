@@ -93,6 +93,10 @@ def test_step_op_entry_points_report_errors_without_gpu():
     assert b"null pointer" in lib.vp3d_last_error()
     assert lib.vp3d_mpjpe_fwd_bwd(None, None, None, 4, 3, None, None, None) == -1
     assert lib.vp3d_mpjpe_fwd_bwd(None, None, None, 4, 0, None, None, None) == -1
+    assert lib.vp3d_projected_mpjpe_fwd_bwd(None, None, None, None, 4, 1, 17, 0, None, None, None,
+                                            None) == -1
+    assert lib.vp3d_projected_mpjpe_fwd_bwd(None, None, None, None, 4, 0, 17, 0, None, None, None,
+                                            None) == -1
 
 
 def test_fused_adam_contract_without_gpu():

@@ -149,3 +149,46 @@ def test_weighted_mpjpe_matches_reference_formula(cuda_device):
     ours.backward()
     assert abs(float(ours) - float(ref)) <= 2e-6 * abs(float(ref))
     assert _close(pred.grad, ref_in.grad, 1e-5, 1e-10)
+
+
+def _project_reference(X, cam, linear):
+    """Plain torch restatement of the H3.6M projection (common/camera.py:37-88)."""
+    cp = cam[:, None, None, :]
+    f, c, k, p = cp[..., :2], cp[..., 2:4], cp[..., 4:7], cp[..., 7:]
+    XX = torch.clamp(X[..., :2] / X[..., 2:], min=-1, max=1)
+    if linear:
+        return f * XX + c
+    r2 = torch.sum(XX ** 2, dim=-1, keepdim=True)
+    radial = 1 + torch.sum(k * torch.cat((r2, r2 ** 2, r2 ** 3), dim=-1), dim=-1, keepdim=True)
+    tan = torch.sum(p * XX, dim=-1, keepdim=True)
+    return f * (XX * (radial + tan) + p * r2) + c
+
+
+@pytest.mark.parametrize("linear", [False, True])
+def test_projected_mpjpe_matches_reference_formula(cuda_device, linear):
+    """Semi-supervised reconstruction loss (run.py:374-379) and both gradients against autograd
+    through the plain torch formula: loss 2e-6 relative, gradients 1e-5 relative + 1e-8 absolute (typical gradient 3e-5)."""
+    g = torch.Generator().manual_seed(7)
+    n, t, j = 512, 1, 17
+    pos = (torch.randn(n, t, j, 3, generator=g) * 0.3).to(cuda_device)
+    traj = (torch.randn(n, t, 1, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 4.5])).to(cuda_device)
+    with torch.no_grad():
+        pos[0, 0, 0, 0] = 9.0    # beyond the [-1, 1] clamp: no gradient through x
+        pos[1, 0, 3, 1] = -9.0
+    cam = torch.cat([torch.rand(n, 2, generator=g) + 1.0, torch.rand(n, 2, generator=g) * 0.1,
+                     torch.randn(n, 3, generator=g) * 0.1, torch.randn(n, 2, generator=g) * 0.01],
+                    dim=1).to(cuda_device)
+    target = (torch.randn(n, t, j, 2, generator=g) * 0.3).to(cuda_device)
+    pa, ta = pos.clone().requires_grad_(True), traj.clone().requires_grad_(True)
+    pb, tb = pos.clone().requires_grad_(True), traj.clone().requires_grad_(True)
+    ref = torch.mean(torch.norm(_project_reference(pb + tb, cam, linear) - target, dim=-1))
+    ref.backward()
+    ours = vloss.projected_mpjpe(pa, ta, cam, target, linear=linear)
+    ours.backward()
+    assert abs(ours.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert float(pa.grad[0, 0, 0, 0]) == 0.0 and float(pa.grad[1, 0, 3, 1]) == 0.0
+    assert _close(pa.grad, pb.grad, 1e-5, 1e-8)
+    assert _close(ta.grad, tb.grad, 1e-5, 1e-8)
+    with torch.no_grad():
+        assert abs(vloss.projected_mpjpe(pos, traj, cam, target, linear=linear).item() - ref.item()) \
+            <= 2e-6 * abs(ref.item())

@@ -122,6 +122,89 @@ mpjpe_kernel(const float* __restrict__ pred, const float* __restrict__ target,
   }
 }
 
+// ---- re-projection loss (semi-supervised branch) -------------------------------------------------
+
+// One thread per frame (n, t): for each joint X = pos + traj, project with the camera of sample n
+// (camera.py:37-67: perspective divide clamped to [-1, 1], radial k1..k3 and tangential p1, p2
+// distortion, focal length, principal point; or only the linear part, :69-88), accumulate the 2-D
+// distance to the target, and write d loss / d pos per joint and d loss / d traj per frame (the
+// joint sum -- no atomics needed since the frame's joints live in one thread).
+__global__ void __launch_bounds__(kLossThreads)
+projected_mpjpe_kernel(const float* __restrict__ pos, const float* __restrict__ traj,
+                       const float* __restrict__ cam, const float* __restrict__ target,
+                       float* __restrict__ dpos, float* __restrict__ dtraj, float* __restrict__ loss,
+                       long long frames_total, int frames_per_sample, int joints, int linear,
+                       float weight) {
+  __shared__ float s_part[kLossThreads / 32];
+  const long long fr = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+  float acc = 0.0f;
+  if (fr < frames_total) {
+    const float* cp = cam + (fr / frames_per_sample) * 9;
+    const float fx = cp[0], fy = cp[1], cx = cp[2], cy = cp[3];
+    const float k0 = cp[4], k1 = cp[5], k2 = cp[6], p0 = cp[7], p1 = cp[8];
+    const float tx = traj[fr * 3 + 0], ty = traj[fr * 3 + 1], tz = traj[fr * 3 + 2];
+    float gtx = 0.0f, gty = 0.0f, gtz = 0.0f;
+    for (int j = 0; j < joints; ++j) {
+      const long long e = fr * joints + j;
+      const float x = pos[e * 3 + 0] + tx, y = pos[e * 3 + 1] + ty, z = pos[e * 3 + 2] + tz;
+      const float u = x / z, v = y / z;
+      const float xx = fminf(fmaxf(u, -1.0f), 1.0f), yy = fminf(fmaxf(v, -1.0f), 1.0f);
+      float ox, oy;           // projected point before focal length / principal point
+      float s = 1.0f, rp = 0.0f, r2 = 0.0f;
+      if (linear) {
+        ox = xx;
+        oy = yy;
+      } else {
+        r2 = xx * xx + yy * yy;
+        const float radial = 1.0f + r2 * (k0 + r2 * (k1 + r2 * k2));
+        rp = k0 + r2 * (2.0f * k1 + 3.0f * k2 * r2);  // d radial / d r2
+        s = radial + (p0 * xx + p1 * yy);
+        ox = xx * s + p0 * r2;
+        oy = yy * s + p1 * r2;
+      }
+      const float ex = fx * ox + cx - target[e * 2 + 0];
+      const float ey = fy * oy + cy - target[e * 2 + 1];
+      const float d = sqrtf(ex * ex + ey * ey);
+      acc += d;
+      if (dpos != nullptr) {
+        const float inv = d > 0.0f ? weight / d : 0.0f;
+        const float a = fx * ex * inv, b = fy * ey * inv;  // d loss / d (ox, oy)
+        float gxx, gyy;
+        if (linear) {
+          gxx = a;
+          gyy = b;
+        } else {
+          const float sx = rp * 2.0f * xx + p0, sy = rp * 2.0f * yy + p1;  // d s / d (xx, yy)
+          gxx = a * (s + xx * sx + p0 * 2.0f * xx) + b * (yy * sx + p1 * 2.0f * xx);
+          gyy = a * (xx * sy + p0 * 2.0f * yy) + b * (s + yy * sy + p1 * 2.0f * yy);
+        }
+        const float gu = (u >= -1.0f && u <= 1.0f) ? gxx : 0.0f;  // clamp passes gradient inside
+        const float gv = (v >= -1.0f && v <= 1.0f) ? gyy : 0.0f;
+        const float gx = gu / z, gy = gv / z, gz = -(gu * u + gv * v) / z;
+        dpos[e * 3 + 0] = gx;
+        dpos[e * 3 + 1] = gy;
+        dpos[e * 3 + 2] = gz;
+        gtx += gx;
+        gty += gy;
+        gtz += gz;
+      }
+    }
+    if (dtraj != nullptr) {
+      dtraj[fr * 3 + 0] = gtx;
+      dtraj[fr * 3 + 1] = gty;
+      dtraj[fr * 3 + 2] = gtz;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kLossThreads / 32 ? s_part[threadIdx.x] : 0.0f;
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss, v * weight);
+  }
+}
+
 }  // namespace
 }  // namespace vp3d
 
@@ -193,6 +276,33 @@ VP3D_EXPORT int vp3d_mpjpe_fwd_bwd(const float* pred, const float* target, const
   if (blocks > 0x7fffffffll) return fail(VP3D_ERR_UNSUPPORTED, "vp3d_mpjpe_fwd_bwd: too large");
   mpjpe_kernel<<<(unsigned)blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
       pred, target, joint_w, dpred, loss, joints_total, dims, (float)(1.0 / (double)joints_total));
+  CUDA_TRY(cudaGetLastError());
+  return VP3D_OK;
+}
+
+VP3D_EXPORT int vp3d_projected_mpjpe_fwd_bwd(const float* pos, const float* traj, const float* cam,
+                                             const float* target, int64_t samples,
+                                             int32_t frames_per_sample, int32_t joints,
+                                             int32_t linear, float* loss, float* dpos, float* dtraj,
+                                             void* stream) {
+  using namespace vp3d;
+  if (samples < 0 || frames_per_sample < 1 || joints < 1)
+    return fail(VP3D_ERR_INVALID, "vp3d_projected_mpjpe_fwd_bwd: bad sizes (samples %lld, frames %d, "
+                "joints %d)", (long long)samples, frames_per_sample, joints);
+  if (loss == nullptr) return fail(VP3D_ERR_INVALID, "vp3d_projected_mpjpe_fwd_bwd: null loss pointer");
+  if ((dpos == nullptr) != (dtraj == nullptr))
+    return fail(VP3D_ERR_INVALID, "vp3d_projected_mpjpe_fwd_bwd: dpos and dtraj go together");
+  if (samples > 0 && (!pos || !traj || !cam || !target))
+    return fail(VP3D_ERR_INVALID, "vp3d_projected_mpjpe_fwd_bwd: null pointer");
+  CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  if (samples == 0) return VP3D_OK;
+  const long long frames_total = samples * frames_per_sample;
+  const long long blocks = (frames_total + kLossThreads - 1) / kLossThreads;
+  if (blocks > 0x7fffffffll)
+    return fail(VP3D_ERR_UNSUPPORTED, "vp3d_projected_mpjpe_fwd_bwd: too large");
+  projected_mpjpe_kernel<<<(unsigned)blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
+      pos, traj, cam, target, dpos, dtraj, loss, frames_total, frames_per_sample, joints, linear,
+      (float)(1.0 / ((double)frames_total * joints)));
   CUDA_TRY(cudaGetLastError());
   return VP3D_OK;
 }

@@ -1,15 +1,19 @@
-"""Fused position losses (position part).
+"""Fused losses.
 
 `mpjpe` and `weighted_mpjpe` with the reference's signatures and values (common/loss.py:11-17,
 :19-25; used at run.py:359, 413, 452, 501): the loss and its gradient with respect to the
 prediction come out of ONE launch (`vp3d_mpjpe_fwd_bwd`, csrc/step_ops.cu) instead of the
-subtract / norm / mean kernels and their four backward kernels.  CUDA float32 only, no fallback.
+subtract / norm / mean kernels and their four backward kernels.  `projected_mpjpe` is the
+re-projection loss of the semi-supervised branch (run.py:374-379): camera projection of
+`predicted_pos + predicted_traj` (common/camera.py:37-88) and the 2-D mpjpe, with the gradients for
+both model outputs, in one launch (`vp3d_projected_mpjpe_fwd_bwd`).  CUDA float32 only, no
+fallback; the bone-length penalty (run.py:385-390) stays on stock torch ops.
 """
 import torch
 
 from . import _capi
 
-__all__ = ["mpjpe", "weighted_mpjpe"]
+__all__ = ["mpjpe", "weighted_mpjpe", "projected_mpjpe"]
 
 
 class _Mpjpe(torch.autograd.Function):
@@ -58,3 +62,47 @@ def weighted_mpjpe(predicted, target, w):
     assert predicted.shape == target.shape
     assert w.shape[0] == predicted.shape[0]
     return _Mpjpe.apply(predicted, target, w)
+
+
+class _ProjectedMpjpe(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, traj, cam, target, linear):
+        for t, what in ((pos, "predicted_pos"), (traj, "predicted_traj"), (cam, "camera_params"),
+                        (target, "target_2d")):
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise RuntimeError(f"videopose3d_b200.loss: {what} must be a CUDA float32 tensor "
+                                   f"(got {t.device}, {t.dtype}); there is no fallback path")
+        n, frames, joints = pos.shape[0], pos.shape[1], pos.shape[2]
+        assert pos.dim() == 4 and pos.shape[-1] == 3
+        assert traj.shape == (n, frames, 1, 3), traj.shape
+        assert cam.shape == (n, 9), cam.shape                      # camera.py:47-49
+        assert target.shape == (n, frames, joints, 2), target.shape
+        lib = _capi.load()
+        pos_c, traj_c, cam_c, tgt_c = (t.contiguous() for t in (pos, traj, cam, target))
+        loss = torch.empty((), dtype=torch.float32, device=pos.device)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dpos = torch.empty_like(pos_c) if need_grad else None
+        dtraj = torch.empty_like(traj_c) if need_grad else None
+        with torch.cuda.device(pos.device):
+            stream = torch.cuda.current_stream(pos.device).cuda_stream
+            _capi.check(lib.vp3d_projected_mpjpe_fwd_bwd(
+                pos_c.data_ptr(), traj_c.data_ptr(), cam_c.data_ptr(), tgt_c.data_ptr(), n, frames,
+                joints, int(bool(linear)), loss.data_ptr(),
+                dpos.data_ptr() if need_grad else None, dtraj.data_ptr() if need_grad else None,
+                stream), "vp3d_projected_mpjpe_fwd_bwd")
+        ctx.grads = (dpos, dtraj)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dpos, dtraj = ctx.grads
+        ctx.grads = None
+        if dpos is None:
+            return None, None, None, None, None
+        return dpos * grad_out, dtraj * grad_out, None, None, None
+
+
+def projected_mpjpe(predicted_pos, predicted_traj, camera_params, target_2d, linear=False):
+    """`mpjpe(project_to_2d(predicted_pos + predicted_traj, camera_params), target_2d)` -- the
+    reconstruction loss of run.py:374-379 (`project_to_2d_linear` when `linear`)."""
+    return _ProjectedMpjpe.apply(predicted_pos, predicted_traj, camera_params, target_2d, linear)
