@@ -130,11 +130,11 @@ def test_mpjpe_matches_reference_formula(cuda_device):
     ref.backward()
     ours = vloss.mpjpe(pred, tgt)
     (ours * 3.0).backward()
-    assert ours.shape == () and abs(float(ours) - float(ref)) <= 2e-6 * float(ref)
+    assert ours.shape == () and abs(ours.item() - ref.item()) <= 2e-6 * ref.item()
     assert torch.isfinite(pred.grad).all() and float(pred.grad[3, 0, 5].abs().max()) == 0.0
     assert _close(pred.grad, 3.0 * ref_in.grad, 1e-5, 1e-10)
     with torch.no_grad():  # evaluation use (run.py:452): no gradient buffer, same value
-        assert abs(float(vloss.mpjpe(pred, tgt)) - float(ref)) <= 2e-6 * float(ref)
+        assert abs(vloss.mpjpe(pred, tgt).item() - ref.item()) <= 2e-6 * ref.item()
 
 
 def test_weighted_mpjpe_matches_reference_formula(cuda_device):
@@ -147,7 +147,7 @@ def test_weighted_mpjpe_matches_reference_formula(cuda_device):
     ref.backward()
     ours = vloss.weighted_mpjpe(pred, tgt, w)
     ours.backward()
-    assert abs(float(ours) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert abs(ours.item() - ref.item()) <= 2e-6 * abs(ref.item())
     assert _close(pred.grad, ref_in.grad, 1e-5, 1e-10)
 
 
