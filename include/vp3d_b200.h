@@ -235,6 +235,11 @@ typedef struct {
   float bnb_p;          /* its dropout probability */
   unsigned long long bnb_seed;
   int bnb_layer;
+  /* out_planes == 2, flat tiling: rows [lo_row_begin, lo_row_end) are the only ones whose lo plane
+   * a later stage reads (residual sources in the tap-major row order); tiles outside skip it.
+   * lo_row_end == 0 means every row. */
+  int lo_row_begin;
+  int lo_row_end;
 } vp3d_conv_desc;
 
 int vp3d_conv_gemm(const vp3d_conv_desc* d, void* stream);

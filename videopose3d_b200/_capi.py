@@ -141,6 +141,8 @@ class ConvDesc(ctypes.Structure):
         ("bnb_p", ctypes.c_float),
         ("bnb_seed", ctypes.c_ulonglong),
         ("bnb_layer", ctypes.c_int),
+        ("lo_row_begin", ctypes.c_int),
+        ("lo_row_end", ctypes.c_int),
     ]
 
 

@@ -193,6 +193,8 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   g.out_f32_ld = d->out_f32_ld;
   g.n_valid = d->n_valid > 0 ? d->n_valid : d->n_pad;
   g.stats = d->stats;
+  g.lo_row_begin = d->lo_row_end > 0 ? d->lo_row_begin : 0;
+  g.lo_row_end = d->lo_row_end > 0 ? d->lo_row_end : 0x7fffffff;
   if (!d->out && !d->out_f32) return fail(VP3D_ERR_INVALID, "conv_gemm: no output");
   if (d->out && (d->out_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: out_ld % 8 != 0");
   if (d->res && (d->res_ld % 8)) return fail(VP3D_ERR_INVALID, "conv_gemm: res_ld % 8 != 0");
@@ -601,9 +603,37 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   };
 
   // ---- input packing + expand conv (model.py:127 / :188)
+  // Strided schedule: every activation is kept in tap-major row order (pack.cuh), so the w taps
+  // of block i are w contiguous row regions of R[i] = N * L[i] rows: tap k of output row j is row
+  // k * R[i] + j of the block input, and the residual of the block is its centre (or, causal, last)
+  // region.  Only that region of X needs the lo plane in `mixed` mode.
+  long long R[VP3D_MAX_WIDTHS];
+  for (int i = 0; i <= p->nb; ++i) R[i] = (long long)N * L[i];
+  auto lo_rows = [&](int i, vp3d_conv_desc& q) {  // q produces X_i
+    q.lo_row_begin = 0;
+    q.lo_row_end = 0;  // every row
+    if (!strided || p->planes != 2 || i >= p->nb || x3[i + 1]) return;
+    const long long c = fw[i + 1] / 2 + p->shift_str[i + 1];
+    q.lo_row_begin = (int)(c * R[i + 1]);
+    q.lo_row_end = (int)((c + 1) * R[i + 1]);
+  };
   if (strided) {
+    if ((long long)N * L[0] > 0x7fffffffll)
+      return fail(VP3D_ERR_UNSUPPORTED, "forward_eval: too many rows (%lld)", (long long)N * L[0]);
+    PackPerm perm;
+    memset(&perm, 0, sizeof(perm));
+    perm.levels = p->nb;
+    perm.last_rows = L[p->nb];
+    for (int i = 1; i <= p->nb; ++i) {
+      if (L[i - 1] != fw[i] * L[i])  // trailing frames that do not fill a stride group
+        return fail(VP3D_ERR_UNSUPPORTED,
+                    "strided schedule needs layer lengths divisible by the filter width "
+                    "(block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
+      perm.region[i - 1] = R[i];
+      perm.width[i - 1] = fw[i];
+    }
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
-                               (long long)wl.a0_plane, stream)));
+                               (long long)wl.a0_plane, stream, &perm)));
     common(d, x3[0]);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
@@ -618,6 +648,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   }
   d.scale = p->expand_dil.scale; d.shift = p->expand_dil.shift; d.relu = 1;
   d.out = xb[0]; d.out_plane_stride = (long long)wl.x_plane; d.out_ld = C;
+  lo_rows(0, d);
   VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
 
   // ---- residual blocks (model.py:129-135 / :190-194)
@@ -635,19 +666,10 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     d.w = c0.w; d.taps = c0.taps; d.k_per_tap = C; d.n_pad = C;
     d.scale = c0.scale; d.shift = c0.shift; d.relu = 1;
     d.out = hb; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
-    bool exact = false;
     if (strided) {
-      exact = (Lin == fw[i] * Lout);
-      d.tap_col_step = C; d.tap_row_step = 0;
-      if (exact) {
-        d.samples = 1; d.a_rows = N * Lout; d.a_ld = fw[i] * C;
-        d.per_sample_tiles = 0; d.out_rows = N * Lout;
-      } else {
-        // trailing frames that do not fill a stride group are dropped (Conv1d floor semantics)
-        return fail(VP3D_ERR_UNSUPPORTED,
-                    "strided schedule needs layer lengths divisible by the filter width "
-                    "(block %d: %d frames, width %d)", i, Lin, fw[i]);
-      }
+      d.tap_col_step = 0; d.tap_row_step = (int)R[i];  // tap k = row region k of the block input
+      d.samples = 1; d.a_rows = N * Lin; d.a_ld = C;
+      d.per_sample_tiles = 0; d.out_rows = N * Lout;
     } else {
       d.samples = N; d.a_rows = Lin; d.a_ld = C;
       d.per_sample_tiles = 1; d.tap_row_step = p->dilation[i]; d.tap_col_step = 0;
@@ -667,8 +689,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     d.scale = c1.scale; d.shift = c1.shift; d.relu = 1;
     d.res = xb[cur]; d.res_plane_stride = (long long)cur_plane; d.res_ld = C;
     if (strided) {
-      d.res_rows_per_sample = 0; d.res_row_step = fw[i];
-      d.res_row_off = fw[i] / 2 + p->shift_str[i]; d.res_sample_div = 0;
+      d.res_rows_per_sample = 0; d.res_row_step = 1;
+      d.res_row_off = (int)((fw[i] / 2 + p->shift_str[i]) * R[i]); d.res_sample_div = 0;
     } else {
       // per-sample tiles: the residual rows of a tile are then one TMA box of the block input
       d.samples = N; d.a_rows = Lout; d.per_sample_tiles = 1; d.out_rows = Lout;
@@ -676,6 +698,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       d.res_row_off = p->pad[i] + p->shift_dil[i]; d.res_sample_div = 0;
     }
     d.out = xb[cur ^ 1]; d.out_plane_stride = (long long)h_plane; d.out_ld = C;
+    lo_rows(i, d);
     VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
     cur ^= 1;
     cur_plane = h_plane;

@@ -306,6 +306,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         res_row = (long long)rsmp * p.res_rows_per_sample + in_sample;
       }
 
+      // lo plane only where somebody reads it (tile-uniform)
+      const bool two_planes_t =
+          two_planes && (p.dilated || (row0 < p.lo_row_end && row0 + kBlockM > p.lo_row_begin));
+
       // Both groups wait for the accumulator even when a tile holds no block for one of them: the
       // release below must not run ahead of the MMAs that refill this TMEM stage.
       mbar_wait(tfull_bar + acc * 8, acc_phase);
@@ -398,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int q = 0; q < 4; ++q)
               st_shared_v4(my_store + stage_row + (((half * 4 + q) ^ sw) << 4), hi[4 * q],
                            hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (two_planes) {
+            if (two_planes_t) {
               uint32_t lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -417,7 +421,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               group_bar_sync(bar_id);
               if (store_leader) {
                 tma_store_4d(&tmap_out, my_store, cb, row0, sample, 0);
-                if (two_planes) tma_store_4d(&tmap_out, my_store + Cfg::kTileBytes, cb, row0, sample, 1);
+                if (two_planes_t)
+                  tma_store_4d(&tmap_out, my_store + Cfg::kTileBytes, cb, row0, sample, 1);
                 tma_store_commit();
               }
             }

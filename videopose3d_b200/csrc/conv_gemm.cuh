@@ -90,6 +90,9 @@ struct ConvGemmArgs {
   int out_f32_ld;
   int n_valid;                 // number of real output channels (<= n_pad)
   float* stats;                // [2][n_pad] running sum / sumsq accumulators (atomicAdd)
+  // two output planes: the lo plane is only produced for tiles that intersect rows
+  // [lo_row_begin, lo_row_end) (flat tiling; the rows a later residual add / split-bf16 GEMM reads)
+  int lo_row_begin, lo_row_end;
 };
 
 // Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);

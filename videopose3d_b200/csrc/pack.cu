@@ -1,5 +1,7 @@
 #include "pack.cuh"
 
+#include <string.h>
+
 #include <stdint.h>
 
 namespace vp3d {
@@ -12,7 +14,8 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 // One thread per (row, 8-column group): 16-byte stores, coalesced along the row.
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                   int planes, int N, int T, int c_raw, int rows, int group,
-                                  int frame_step, int k_pad, long long plane_stride) {
+                                  int frame_step, int k_pad, long long plane_stride,
+                                  const PackPerm perm) {
   const int groups_per_row = k_pad >> 3;
   const long long total = (long long)N * rows * groups_per_row;
   const int k_valid = group * c_raw;
@@ -20,8 +23,22 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
        i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups_per_row);
     const long long row = i / groups_per_row;
-    const int r = (int)(row % rows);
-    const int n = (int)(row / rows);
+    int r, n;
+    if (perm.levels == 0) {
+      r = (int)(row % rows);
+      n = (int)(row / rows);
+    } else {
+      // tap-major order: peel one tap digit per block, outermost first, then rebuild the frame
+      long long j = row;
+      int digit[8];
+      for (int i = 0; i < perm.levels; ++i) {
+        digit[i] = (int)(j / perm.region[i]);
+        j -= digit[i] * perm.region[i];
+      }
+      n = (int)(j / perm.last_rows);
+      r = (int)(j - (long long)n * perm.last_rows);
+      for (int i = perm.levels - 1; i >= 0; --i) r = r * perm.width[i] + digit[i];
+    }
     const float* src = x + ((long long)n * T + (long long)r * frame_step) * c_raw;
     __align__(16) __nv_bfloat16 hi[8];
     __align__(16) __nv_bfloat16 lo[8];
@@ -39,14 +56,17 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
 
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
                               int c_raw, int rows, int group, int frame_step, int k_pad,
-                              long long plane_stride, cudaStream_t stream) {
+                              long long plane_stride, cudaStream_t stream, const PackPerm* perm) {
+  PackPerm pp;
+  memset(&pp, 0, sizeof(pp));
+  if (perm) pp = *perm;
   const long long total = (long long)N * rows * (k_pad >> 3);
   if (total <= 0) return cudaSuccess;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_input_kernel<<<(int)blocks, threads, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
-                                                         frame_step, k_pad, plane_stride);
+                                                         frame_step, k_pad, plane_stride, pp);
   return cudaGetLastError();
 }
 

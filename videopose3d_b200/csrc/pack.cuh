@@ -12,9 +12,22 @@ namespace vp3d {
 // at frame r*frame_step, i.e. columns [0, group*c_raw) = x[n, r*frame_step : r*frame_step+group, :]
 // flattened, zero padded to k_pad.  (group = 1, frame_step = 1 for the dilated layout; group =
 // frame_step = w0 for the strided layout where expand_conv becomes a plain GEMM.)
+//
+// Row order.  Default (perm == nullptr or perm->levels == 0): row index = n*rows + r.  Tap-major
+// order (eval strided schedule): the rows of every activation are ordered so that the `w` taps of
+// the next strided conv are `w` contiguous row regions.  With block widths w_1..w_B and
+// R_i = N * rows_out(block i):  pos_0(n, t0) = (t0 mod w_1)*R_1 + pos_1(n, t0 / w_1), ...,
+// pos_B(n, t) = n*rows_out(B) + t.  `perm` carries (R_i, w_i) for i = 1..levels and rows_out(B).
+struct PackPerm {
+  int levels;        // number of residual blocks B (0 = natural order)
+  int last_rows;     // rows per sample after the last block
+  long long region[8];  // R_1 .. R_B
+  int width[8];         // w_1 .. w_B
+};
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
                               int c_raw, int rows, int group, int frame_step, int k_pad,
-                              long long plane_stride, cudaStream_t stream);
+                              long long plane_stride, cudaStream_t stream,
+                              const PackPerm* perm = nullptr);
 
 // w: fp32 Conv1d weight (c_out, c_in, taps) (tap index innermost, model.py:102,113-118).
 // out: bf16 [planes][taps_out][n_pad][k_pad], zero padded.
