@@ -629,7 +629,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
         return fail(VP3D_ERR_UNSUPPORTED,
                     "strided schedule needs layer lengths divisible by the filter width "
                     "(block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
-      perm.region[i - 1] = R[i];
+      perm.region[i - 1] = (unsigned)R[i];
       perm.width[i - 1] = fw[i];
     }
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,

@@ -21,23 +21,40 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
   const int k_valid = group * c_raw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups_per_row);
-    const long long row = i / groups_per_row;
+    int g;
+    long long row;
+    if (total < 0x7fffffffll) {  // 32-bit index math (the common case): far cheaper divisions
+      const unsigned iu = (unsigned)i;
+      const unsigned ru = iu / (unsigned)groups_per_row;
+      g = (int)(iu - ru * (unsigned)groups_per_row);
+      row = ru;
+    } else {
+      g = (int)(i % groups_per_row);
+      row = i / groups_per_row;
+    }
     int r, n;
     if (perm.levels == 0) {
-      r = (int)(row % rows);
-      n = (int)(row / rows);
-    } else {
-      // tap-major order: peel one tap digit per block, outermost first, then rebuild the frame
-      long long j = row;
-      int digit[8];
-      for (int i = 0; i < perm.levels; ++i) {
-        digit[i] = (int)(j / perm.region[i]);
-        j -= digit[i] * perm.region[i];
+      if (total < 0x7fffffffll) {
+        n = (int)((unsigned)row / (unsigned)rows);
+        r = (int)((unsigned)row - (unsigned)n * (unsigned)rows);
+      } else {
+        r = (int)(row % rows);
+        n = (int)(row / rows);
       }
-      n = (int)(j / perm.last_rows);
-      r = (int)(j - (long long)n * perm.last_rows);
-      for (int i = perm.levels - 1; i >= 0; --i) r = r * perm.width[i] + digit[i];
+    } else {
+      // tap-major order (row < 2^31): peel one tap digit per block, outermost first; digit i has
+      // weight w_1 * ... * w_(i-1) in the frame index, the in-sample row of the last block the
+      // product of all widths
+      unsigned j = (unsigned)row;
+      int frame = 0, weight = 1;
+      for (int lv = 0; lv < perm.levels; ++lv) {
+        const unsigned dgt = j / perm.region[lv];
+        j -= dgt * perm.region[lv];
+        frame += (int)dgt * weight;
+        weight *= perm.width[lv];
+      }
+      n = (int)(j / (unsigned)perm.last_rows);
+      r = frame + (int)(j - (unsigned)n * (unsigned)perm.last_rows) * weight;
     }
     const float* src = x + ((long long)n * T + (long long)r * frame_step) * c_raw;
     __align__(16) __nv_bfloat16 hi[8];

@@ -21,7 +21,7 @@ namespace vp3d {
 struct PackPerm {
   int levels;        // number of residual blocks B (0 = natural order)
   int last_rows;     // rows per sample after the last block
-  long long region[8];  // R_1 .. R_B
+  unsigned region[8];   // R_1 .. R_B  (row counts < 2^31)
   int width[8];         // w_1 .. w_B
 };
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
