@@ -40,6 +40,36 @@ def test_struct_sizes_match_header_layout():
     assert _capi.ctypes.sizeof(_capi.Weights) == 8 * (1 + 4 + 14 + 56 + 2)
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct the Python host passes by pointer, measured by compiling the
+    public header with the C compiler, against the ctypes mirrors in _capi.py."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    ct = _capi.ctypes
+    pairs = {"vp3d_config": _capi.Config, "vp3d_weights": _capi.Weights, "vp3d_grads": _capi.Grads,
+             "vp3d_conv_desc": _capi.ConvDesc, "vp3d_gather_desc": _capi.GatherDesc,
+             "vp3d_adam_tensor": _capi.AdamTensor}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vp3d_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    include = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call([cc, "-std=c99", "-I", include, str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == ct.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 def test_plan_create_reports_errors_without_gpu():
     lib = _capi.load()
     cfg = _capi.Config()
