@@ -417,6 +417,7 @@ def run_ours(args, rank, local_rank, world):
             "executed_tflops_per_s": FLOPS_PER_SAMPLE_CONE * N_PER_GPU * world * args.steps / (total_ms * 1e-3) / 1e12,
             "dense_equivalent_tflops_per_s": FLOPS_PER_SAMPLE_DENSE * N_PER_GPU * world * args.steps / (total_ms * 1e-3) / 1e12,
             "wall_s_timed_region": t_wall,
+            "input_frames_per_s": value * T,   # secondary column of SURVEY §8d: N*T / time
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
