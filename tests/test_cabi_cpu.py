@@ -203,3 +203,19 @@ def test_no_cpu_fallback():
         m(torch.zeros(2, 27, 17, 2))
     with pytest.raises(AssertionError, match="odd filter widths"):
         vp.TemporalModelOptimized1f(17, 2, 17, [3, 2])
+
+
+def test_bone_length_penalty_matches_inline_reference_formula():
+    """run.py:385-390 restated inline (plain torch, runs anywhere)."""
+    from videopose3d_b200.loss import bone_length_penalty
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randn(12, 3, 17, 3, generator=g, requires_grad=True)
+    parents = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15]   # h36m 17-joint skeleton
+    split = 7
+    dists = pred[:, :, 1:] - pred[:, :, parents[1:]]
+    lengths = torch.mean(torch.norm(dists, dim=3), dim=1)
+    ref = torch.mean(torch.abs(torch.mean(lengths[:split], dim=0) - torch.mean(lengths[split:], dim=0)))
+    ours = bone_length_penalty(pred, split, parents)
+    assert torch.allclose(ours, ref, rtol=0, atol=0)
+    ours.backward()
+    assert pred.grad is not None and torch.isfinite(pred.grad).all()

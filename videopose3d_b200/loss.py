@@ -7,13 +7,13 @@ subtract / norm / mean kernels and their four backward kernels.  `projected_mpjp
 re-projection loss of the semi-supervised branch (run.py:374-379): camera projection of
 `predicted_pos + predicted_traj` (common/camera.py:37-88) and the 2-D mpjpe, with the gradients for
 both model outputs, in one launch (`vp3d_projected_mpjpe_fwd_bwd`).  CUDA float32 only, no
-fallback; the bone-length penalty (run.py:385-390) stays on stock torch ops.
+fallback.  `bone_length_penalty` (run.py:385-390) is composed from torch ops.
 """
 import torch
 
 from . import _capi
 
-__all__ = ["mpjpe", "weighted_mpjpe", "projected_mpjpe"]
+__all__ = ["mpjpe", "weighted_mpjpe", "projected_mpjpe", "bone_length_penalty"]
 
 
 class _Mpjpe(torch.autograd.Function):
@@ -106,3 +106,15 @@ def projected_mpjpe(predicted_pos, predicted_traj, camera_params, target_2d, lin
     """`mpjpe(project_to_2d(predicted_pos + predicted_traj, camera_params), target_2d)` -- the
     reconstruction loss of run.py:374-379 (`project_to_2d_linear` when `linear`)."""
     return _ProjectedMpjpe.apply(predicted_pos, predicted_traj, camera_params, target_2d, linear)
+
+
+def bone_length_penalty(predicted_3d_pos_cat, split_idx, parents):
+    """Kinematic term of the semi-supervised branch (run.py:385-390): mean absolute difference
+    between the per-bone mean lengths of the labelled rows `[:split_idx]` and the unlabelled rows
+    `[split_idx:]`.  `parents`: the skeleton's parent index per joint (joint 0 is the root).
+    A handful of tiny reductions on (N, T, J, 3): composed from torch ops, no custom kernel."""
+    parents = list(parents)
+    dists = predicted_3d_pos_cat[:, :, 1:] - predicted_3d_pos_cat[:, :, parents[1:]]
+    bone_lengths = torch.mean(torch.norm(dists, dim=3), dim=1)
+    return torch.mean(torch.abs(torch.mean(bone_lengths[:split_idx], dim=0)
+                                - torch.mean(bone_lengths[split_idx:], dim=0)))
