@@ -381,7 +381,8 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)",
+            "dtype": {"fp16": "fp16 (IEEE fp16 operands and activations, fp32 accumulate)",
+                      "bf16": "bf16", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)",
                       "mixed": "bf16 (residual blocks plain bf16 on a hi+lo residual stream; expand "
                                "and shrink split-bf16; fp32 accumulate)"}[args.precision],
             "data": "synthetic",
@@ -633,7 +634,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "bf16x3"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "mixed", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cudnn", action="store_true",
                     help="skip the informational PyTorch/cuDNN measurement of the reference architecture")

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VP3D_VERSION 100
+#define VP3D_VERSION 200
 #define VP3D_MAX_WIDTHS 8                       /* len(filter_widths) <= 8 (RF up to 3^8) */
 #define VP3D_MAX_LAYERS (2 * (VP3D_MAX_WIDTHS - 1)) /* layers_conv / layers_bn entries */
 
@@ -43,9 +43,14 @@ typedef enum {
 typedef enum {
   VP3D_PRECISION_BF16 = 0,   /* bf16 operands, fp32 accumulate (fast path; BASELINE cfg 2) */
   VP3D_PRECISION_BF16X3 = 1, /* split-bf16 (hi+lo) operands, 3 MMAs per product: fp32-faithful */
-  VP3D_PRECISION_MIXED = 2   /* eval default: bf16 residual blocks, split-bf16 expand and shrink
-                                (and blocks below 0.5% of the FLOPs), residual stream kept in
-                                hi+lo planes; ~1e-3 of fp32 (<= 2e-3) close to bf16 cost */
+  VP3D_PRECISION_MIXED = 2,  /* bf16 residual blocks, split-bf16 expand and shrink (and blocks below
+                                0.5% of the FLOPs), residual stream kept in hi+lo planes; ~1e-3 of
+                                fp32 (<= 2e-3) close to bf16 cost */
+  VP3D_PRECISION_FP16 = 3    /* eval default: IEEE fp16 operands and activations (11-bit significand,
+                                single plane), fp32 accumulate -- the tensor rate of bf16 at 1/8 of
+                                its rounding error: ~4e-4 of fp32 on cfg2, inside north_star's 1e-3.
+                                Stores saturate at +-65504.  Inference only (training runs bf16 /
+                                bf16x3: gradients need the bf16 exponent range) */
 } vp3d_precision;
 
 /* Constructor arguments of TemporalModel / TemporalModelOptimized1f (model.py:85-86, :151-152). */
@@ -198,7 +203,7 @@ typedef struct {
   int tap_row_step;     /* input-row offset between taps (dilation), 0 when taps are column blocks */
   int tap_col_step;     /* input-column offset between taps (strided conv: k_per_tap), else 0 */
   int out_rows;         /* output rows per sample (per_sample_tiles) or in total (flat) */
-  int precision;        /* vp3d_precision */
+  int precision;        /* vp3d_precision (FP16: a, w, res and out hold IEEE fp16, one plane) */
   /* epilogue */
   const float* scale;   /* per channel, may be NULL (-> no affine) */
   const float* shift;

@@ -54,8 +54,8 @@ def conv_gemm(a_planes_t, samples, a_rows, a_ld, w_planes_t, taps, k_per_tap, n_
         d.res_row_off = res_row_off; d.res_sample_div = res_sample_div
     out = out32 = None
     if out_f32_cols is None:
-        out = torch.full((out_planes, total_rows, n_pad), float("nan"), dtype=torch.bfloat16,
-                         device=dev)
+        out = torch.full((out_planes, total_rows, n_pad), float("nan"),
+                         dtype=torch.float16 if precision == 3 else torch.bfloat16, device=dev)
         d.out = out.data_ptr(); d.out_planes = out_planes; d.out_plane_stride = out[0].numel()
         d.out_ld = n_pad
     else:

@@ -19,7 +19,7 @@ for name in golden_names():
     m.load_state_dict(sd)
     m = m.to(dev).eval()
     out = []
-    for prec in ("bf16x3", "mixed", "bf16"):
+    for prec in ("fp16", "bf16x3", "mixed", "bf16"):
         with torch.no_grad():
             y = m.set_precision(prec)(x.to(dev)).cpu().numpy()
         out.append(f"{prec} {np.abs(y - y_ref).max() / np.abs(y_ref).max():.2e}")

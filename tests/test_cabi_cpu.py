@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.vp3d_version() == 100
+    assert lib.vp3d_version() == 200
     assert sorted(_capi.SIGNATURES) == declared
 
 

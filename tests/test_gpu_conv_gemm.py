@@ -145,3 +145,68 @@ def test_stats_accumulation(cuda_device):
     acc = planes_value(a).reshape(M, K) @ planes_value(wp)[0].T
     assert _scale_err(stats[0], acc.sum(0)) < 1e-4
     assert _scale_err(stats[1], (acc * acc).sum(0)) < 1e-4
+
+
+# ---- fp16 operand format (VP3D_PRECISION_FP16 = 3): the eval default
+def _mk16(rows, ld, dev, seed, amp=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = ((torch.rand(rows, ld, generator=g) * 2 - 1) * amp).to(dev)
+    return a.to(torch.float16).unsqueeze(0).contiguous()
+
+
+def _pack16(w, n_pad, k_pad):
+    co, ci, k = w.shape
+    buf = torch.zeros(k, n_pad, k_pad, dtype=torch.float32, device=w.device)
+    buf[:, :co, :ci] = w.permute(2, 0, 1)
+    return buf.to(torch.float16).unsqueeze(0).contiguous()
+
+
+@pytest.mark.parametrize("M,K,n_pad,ncols", [(300, 128, 64, 51), (1000, 1024, 256, 256)])
+def test_fp16_flat_gemm_fp32_out(cuda_device, M, K, n_pad, ncols):
+    dev = cuda_device
+    a = _mk16(M, K, dev, 21)
+    g = torch.Generator().manual_seed(22)
+    w = ((torch.rand(ncols, K, 1, generator=g) * 2 - 1) / K ** 0.5).to(dev)
+    wp = _pack16(w, n_pad, K)
+    _, out = conv_gemm(a, 1, M, K, wp, 1, K, n_pad, per_sample_tiles=False, tap_row_step=0,
+                       tap_col_step=0, out_rows=M, out_f32_cols=ncols, precision=3)
+    exp = (a[0].double() @ wp[0, 0].double().T)[:, :ncols]
+    assert not torch.isnan(out).any()
+    assert _scale_err(out, exp) < 2e-5
+
+
+def test_fp16_strided_conv_residual_fp16_out(cuda_device):
+    """1x1 conv + affine + ReLU + TMA-loaded residual (the block tail of the eval cone schedule) in
+    fp16 storage: result within one fp16 ulp (2^-11 relative) of the fp64 expectation."""
+    dev = cuda_device
+    C, M = 256, 700
+    a = _mk16(M, C, dev, 23)
+    r = _mk16(3 * M, C, dev, 24, amp=4.0)
+    g = torch.Generator().manual_seed(25)
+    w = ((torch.rand(C, C, 1, generator=g) * 2 - 1) / C ** 0.5).to(dev)
+    wp = _pack16(w, C, C)
+    scale = (torch.rand(C, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(C, generator=g) * 0.1).to(dev)
+    out, _ = conv_gemm(a, 1, M, C, wp, 1, C, C, per_sample_tiles=False, tap_row_step=0,
+                       tap_col_step=0, out_rows=M, scale=scale, shift=shift, relu=True, res=r,
+                       res_rows_per_sample=0, res_row_step=1, res_row_off=M, precision=3)
+    acc = a[0].double() @ wp[0, 0].double().T
+    exp = torch.relu(acc * scale.double() + shift.double()) + r[0, M:2 * M].double()
+    got = out[0].double()
+    assert out.dtype == torch.float16 and not torch.isnan(got).any()
+    assert torch.all((got - exp).abs() <= exp.abs() * 2 ** -11 + 1e-6)
+
+
+def test_fp16_store_saturates(cuda_device):
+    """An activation beyond the fp16 range clamps to +-65504 instead of becoming inf."""
+    dev = cuda_device
+    M, K, n_pad = 128, 64, 64
+    a = torch.full((1, M, K), 60.0, dtype=torch.float16, device=dev)
+    w = torch.full((n_pad, K, 1), 30.0, device=dev)
+    w[1::2] *= -1
+    wp = _pack16(w, n_pad, K)
+    out, _ = conv_gemm(a, 1, M, K, wp, 1, K, n_pad, per_sample_tiles=False, tap_row_step=0,
+                       tap_col_step=0, out_rows=M, precision=3)
+    got = out[0].float()
+    assert torch.isfinite(got).all()
+    assert torch.all(got[:, 0::2] == 65504.0) and torch.all(got[:, 1::2] == -65504.0)

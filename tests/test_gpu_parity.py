@@ -2,9 +2,12 @@
 (a) the golden vectors produced by the real reference and (b) the oracle on fresh seeded inputs.
 
 Gates:
-  G1  bf16x3 (fp32-faithful) mode: max|new - ref| / max|ref| <= 1e-3   (measured ~1e-5)
-  G2  bf16 fast mode: same metric <= 3e-2 and |MPJPE(new, y) - MPJPE(ref, y)| <= 0.1 mm on
-      synthetic targets y = ref + N(0, 0.03^2) m, plus mpjpe(new, ref) reported.
+  G1  default (fp16 operands, fp32 accumulate) and bf16x3 (split-bf16) modes:
+      max|new - ref| / max|ref| <= 1e-3 on every golden (north_star's tolerance; measured ~4e-4 /
+      ~1e-5)
+  G2  |MPJPE(new, y) - MPJPE(ref, y)| <= 0.1 mm on synthetic targets y = ref + N(0, 0.03^2) m at
+      BASELINE configs[1] size, plus mpjpe(new, ref) reported
+  secondary modes: `mixed` <= 2e-3 (C = 1024) / 3e-3, pure `bf16` <= 3e-2 (documented, not default)
 """
 import numpy as np
 import pytest
@@ -45,10 +48,29 @@ def test_golden_eval_fp32_faithful(cuda_device, name):
 
 
 @pytest.mark.parametrize("name", EVAL_CASES)
-def test_golden_eval_mixed_default(cuda_device, name):
-    """Default precision mode (bf16 on the FLOP-dominant blocks, split-bf16 elsewhere, exact
+def test_golden_eval_default_fp16(cuda_device, name):
+    """The DEFAULT (and benchmarked) precision mode -- fp16 operands / activations, fp32
+    accumulate -- holds north_star's 1e-3 on every golden produced by the real reference."""
+    meta, sd, x, y_ref, _ = load_golden(name)
+    kw = dict(filter_widths=meta["fw"], causal=meta["causal"], dropout=0.0, channels=meta["C"])
+    if meta["cls"] == "TemporalModel":
+        m = vp.TemporalModel(meta["J"], meta["F"], meta["Jout"], dense=meta["dense"], **kw)
+    else:
+        m = vp.TemporalModelOptimized1f(meta["J"], meta["F"], meta["Jout"], **kw)
+    m.load_state_dict(sd)
+    m = m.to(cuda_device).eval()
+    assert m.precision == "fp16"  # nothing selected: this is what run.py gets
+    with torch.no_grad():
+        y = m(x.to(cuda_device)).cpu()
+    assert tuple(y.shape) == y_ref.shape and y.dtype == torch.float32
+    assert _rel(y.numpy(), y_ref) <= 1e-3
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_golden_eval_mixed(cuda_device, name):
+    """Secondary mode `mixed` (bf16 on the FLOP-dominant blocks, split-bf16 elsewhere, exact
     residual stream): <= 3e-3 of the output scale on every golden (<= 2e-3 on the C = 1024 ones;
-    measured 0.7e-3 .. 1.3e-3 — bf16x3 is the mode that holds the strict 1e-3 gate)."""
+    measured 0.7e-3 .. 1.5e-3 -- which is why it is no longer the default)."""
     meta, sd, x, y_ref, _ = load_golden(name)
     m = _build(meta, sd, cuda_device, "mixed")
     with torch.no_grad():
@@ -71,9 +93,9 @@ def test_golden_eval_bf16(cuda_device, name):
     assert float(orc.mpjpe(y, ref)) <= 1e-2 * scale
 
 
-def test_bf16_mpjpe_gate(cuda_device):
+def test_default_mpjpe_gate(cuda_device):
     """G2 at BASELINE configs[1] size (N = 1024 windows -> 17408 joints): MPJPE of the default
-    (mixed-precision) path
+    (fp16) path
     against synthetic targets y = ref + N(0, 30 mm) differs from the reference's MPJPE by <= 0.1 mm
     (outputs read as metres).  `ref` here is the fp32-faithful CUDA path, itself pinned to the
     reference goldens at <= 1e-3 by test_golden_eval_fp32_faithful."""
@@ -84,18 +106,25 @@ def test_bf16_mpjpe_gate(cuda_device):
     m = _build(meta, sd, cuda_device, "bf16x3")
     with torch.no_grad():
         ref = m(xg).cpu()
-        y = m.set_precision("mixed")(xg).cpu()
+        y = m.set_precision("fp16")(xg).cpu()
         y_pure = m.set_precision("bf16")(xg).cpu()
+        y_mixed = m.set_precision("mixed")(xg).cpu()
     assert _rel(ref[:8].numpy(), y_ref) <= 1e-3
-    # the default (mixed) mode sits at ~1e-3 of fp32 on this workload (bf16x3 is the strict mode)
-    assert _rel(y[:8].numpy(), y_ref) <= 2e-3
-    print(f"pure bf16: mpjpe(bf16,ref)={float(orc.mpjpe(y_pure, ref)) * 1000:.3f} mm")
+    assert _rel(y[:8].numpy(), y_ref) <= 1e-3
+    # whole batch against the fp32-faithful CUDA path (itself <= 1e-3, measured ~1e-5, of the goldens)
+    full = float((y - ref).abs().max() / ref.abs().max())
+    print(f"fp16 vs bf16x3 over 1024 windows: rel {full:.2e}; "
+          f"mixed {float((y_mixed - ref).abs().max() / ref.abs().max()):.2e}; "
+          f"bf16 {float((y_pure - ref).abs().max() / ref.abs().max()):.2e}")
+    assert full <= 1e-3
+    print(f"pure bf16: mpjpe(bf16,ref)={float(orc.mpjpe(y_pure, ref)) * 1000:.3f} mm, "
+          f"mixed: {float(orc.mpjpe(y_mixed, ref)) * 1000:.3f} mm")
     g = torch.Generator().manual_seed(5)
     target = ref + torch.randn(ref.shape, generator=g) * 0.03
     target[:, :, 0] = ref[:, :, 0]
     e_new, e_ref = float(orc.mpjpe(y, target)) * 1000, float(orc.mpjpe(ref, target)) * 1000
     direct = float(orc.mpjpe(y, ref)) * 1000
-    print(f"MPJPE(ref,y)={e_ref:.3f} mm  MPJPE(bf16,y)={e_new:.3f} mm  mpjpe(bf16,ref)={direct:.3f} mm "
+    print(f"MPJPE(ref,y)={e_ref:.3f} mm  MPJPE(fp16,y)={e_new:.3f} mm  mpjpe(fp16,ref)={direct:.3f} mm "
           f"output scale {float(torch.norm(ref, dim=-1).mean()):.3f}")
     assert abs(e_new - e_ref) <= 0.1
 

@@ -16,6 +16,7 @@ VP3D_VARIANT_STRIDED = 1
 VP3D_PRECISION_BF16 = 0
 VP3D_PRECISION_BF16X3 = 1
 VP3D_PRECISION_MIXED = 2
+VP3D_PRECISION_FP16 = 3
 VP3D_PACK_CONV = 1
 VP3D_PACK_BN_EVAL = 2
 VP3D_PACK_CONV_T = 4

@@ -118,6 +118,9 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   if (d->out_rows == 0) return VP3D_OK;
   const int a_planes = d->a_planes > 0 ? d->a_planes : 1;
   const int pairs = d->precision == VP3D_PRECISION_BF16X3 ? 3 : 1;
+  const int f16 = d->precision == VP3D_PRECISION_FP16 ? 1 : 0;
+  if (f16 && (a_planes != 1 || d->out_planes > 1 || d->stats || d->bnb_z))
+    return fail(VP3D_ERR_INVALID, "conv_gemm: fp16 is a single-plane, inference-only format");
   if (pairs == 3 && a_planes != 2)
     return fail(VP3D_ERR_INVALID, "conv_gemm: bf16x3 needs hi/lo planes of A");
   const int w_planes = pairs == 3 ? 2 : 1;
@@ -166,6 +169,7 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   g.n_pad = d->n_pad;
   g.n_tiles = d->n_pad / block_n;
   g.pairs = pairs;
+  g.f16 = f16;
   g.flags = 0;
   if (d->scale && d->shift) g.flags |= kEpiAffine;
   if (d->relu) g.flags |= kEpiRelu;
@@ -309,7 +313,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
   if (cfg->channels < 64 || cfg->channels % 64)
     return fail(VP3D_ERR_UNSUPPORTED, "channels must be a positive multiple of 64 (got %d)",
                 cfg->channels);
-  if (cfg->precision < VP3D_PRECISION_BF16 || cfg->precision > VP3D_PRECISION_MIXED)
+  if (cfg->precision < VP3D_PRECISION_BF16 || cfg->precision > VP3D_PRECISION_FP16)
     return fail(VP3D_ERR_INVALID, "plan_create: unknown precision %d", cfg->precision);
   if (cfg->variant != VP3D_VARIANT_DILATED && cfg->variant != VP3D_VARIANT_STRIDED)
     return fail(VP3D_ERR_INVALID, "plan_create: unknown variant %d", cfg->variant);
@@ -328,7 +332,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
   p->c_in_pad = round_up(p->c_in_raw, 64);
   p->k0_pad = round_up(p->c_in_raw * cfg->filter_widths[0], 64);
   p->c_out_pad = round_up(p->c_out_raw, 64);
-  p->planes = cfg->precision == VP3D_PRECISION_BF16 ? 1 : 2;
+  p->f16 = cfg->precision == VP3D_PRECISION_FP16 ? 1 : 0;
+  p->planes = (cfg->precision == VP3D_PRECISION_BF16 || p->f16) ? 1 : 2;
   // model.py:31, 107-121 / :172-184
   p->pad[0] = cfg->filter_widths[0] / 2;
   p->shift_dil[0] = p->shift_str[0] = cfg->causal ? cfg->filter_widths[0] / 2 : 0;
@@ -423,9 +428,9 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
     if (!w->expand_conv_weight || !w->shrink_weight)
       return fail(VP3D_ERR_INVALID, "set_weights: missing conv weights");
     CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->C,
-                                     p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream));
+                                     p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream, p->f16));
     CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
-                                     p->c_in_raw, w0, p->C, p->k0_pad, 1, stream));
+                                     p->c_in_raw, w0, p->C, p->k0_pad, 1, stream, p->f16));
     // with VP3D_PACK_CONV_T the transposed-pack kernels below also write these forward packs
     const bool fused = (what & VP3D_PACK_CONV_T) != 0;
     for (int i = 0; i < p->nb; ++i) {
@@ -433,13 +438,13 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
         return fail(VP3D_ERR_INVALID, "set_weights: missing layers_conv.%d", 2 * i);
       if (fused) continue;
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i], p->conv[2 * i].w, p->planes,
-                                       p->C, p->C, p->taps[i + 1], p->C, p->C, 0, stream));
+                                       p->C, p->C, p->taps[i + 1], p->C, p->C, 0, stream, p->f16));
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i + 1], p->conv[2 * i + 1].w,
-                                       p->planes, p->C, p->C, 1, p->C, p->C, 0, stream));
+                                       p->planes, p->C, p->C, 1, p->C, p->C, 0, stream, p->f16));
     }
     if (!fused)
       CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw, p->C,
-                                       1, p->c_out_pad, p->C, 0, stream));
+                                       1, p->c_out_pad, p->C, 0, stream, p->f16));
     p->conv_packed = true;
   }
   if (what & VP3D_PACK_BN_EVAL) {
@@ -460,6 +465,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
                                 p->c_out_pad, stream));
     p->bn_packed = true;
   }
+  if ((what & VP3D_PACK_CONV_T) && p->f16)
+    return fail(VP3D_ERR_UNSUPPORTED, "fp16 plans are inference-only (train with bf16 / bf16x3)");
   if (what & VP3D_PACK_CONV_T)
     VP3D_TRY(train_pack_transposed(p, w, stream, (what & VP3D_PACK_CONV) != 0));
   return VP3D_OK;
@@ -587,7 +594,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     fl[p->nb + 1] = (double)N * L[p->nb] * C * p->c_out_raw;
     for (int i = 0; i <= p->nb + 1; ++i) total += fl[i];
     for (int i = 0; i <= p->nb + 1; ++i) {
-      if (p->cfg.precision == VP3D_PRECISION_BF16) x3[i] = false;
+      if (p->cfg.precision == VP3D_PRECISION_BF16 || p->f16) x3[i] = false;
       else if (p->cfg.precision == VP3D_PRECISION_BF16X3) x3[i] = true;
       else x3[i] = (i == 0 || i == p->nb + 1) ? true : (fl[i] < 0.005 * total);
     }
@@ -597,7 +604,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   auto common = [&](vp3d_conv_desc& q, bool layer_x3) {
     memset(&q, 0, sizeof(q));
     q.a_planes = p->planes;
-    q.precision = layer_x3 ? VP3D_PRECISION_BF16X3 : VP3D_PRECISION_BF16;
+    q.precision = p->f16 ? VP3D_PRECISION_FP16
+                         : (layer_x3 ? VP3D_PRECISION_BF16X3 : VP3D_PRECISION_BF16);
     q.out_planes = p->planes;
     q.res_planes = p->planes;
   };
@@ -633,14 +641,14 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       perm.width[i - 1] = fw[i];
     }
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
-                               (long long)wl.a0_plane, stream, &perm)));
+                               (long long)wl.a0_plane, stream, &perm, p->f16)));
     common(d, x3[0]);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
     d.per_sample_tiles = 0; d.out_rows = N * L[0];
   } else {
     VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, T, 1, 1, p->c_in_pad,
-                               (long long)wl.a0_plane, stream)));
+                               (long long)wl.a0_plane, stream, nullptr, p->f16)));
     common(d, x3[0]);
     d.a = a0; d.samples = N; d.a_rows = T; d.a_ld = p->c_in_pad;
     d.w = p->expand_dil.w; d.taps = fw[0]; d.k_per_tap = p->c_in_pad; d.n_pad = C;

@@ -14,6 +14,10 @@
 //                   rows, clipped at the tensor edge by the tensor map)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
 #include "ptx.cuh"
 
 namespace vp3d {
@@ -80,6 +84,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void add_f16x8(float* v, const uint4& u) {
+  v[0] += f16_lo_to_f(u.x);
+  v[1] += f16_hi_to_f(u.x);
+  v[2] += f16_lo_to_f(u.y);
+  v[3] += f16_hi_to_f(u.y);
+  v[4] += f16_lo_to_f(u.z);
+  v[5] += f16_hi_to_f(u.z);
+  v[6] += f16_lo_to_f(u.w);
+  v[7] += f16_hi_to_f(u.w);
+}
+
 __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[0] += bf16_lo_to_f(u.x);
   v[1] += bf16_hi_to_f(u.x);
@@ -91,7 +106,9 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[7] += bf16_hi_to_f(u.w);
 }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+// TRAIN compiles in the training-only epilogue paths (BatchNorm batch statistics of the stored
+// value, fused BatchNorm-backward reductions); eval launches use the leaner TRAIN = false build.
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
@@ -132,7 +149,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // auxiliary tiles per 64-column store block: the residual plane(s) and, for the fused
   // BatchNorm-backward reductions, the Z tile.  kResSlots / tiles stages are in flight.
   const bool has_res = (p.flags & kEpiResidual) != 0;
-  const int aux_tiles = (has_res ? p.res_planes : 0) + (p.bnb ? 1 : 0);
+  const bool bnb = TRAIN && p.bnb != 0;
+  const int aux_tiles = (has_res ? p.res_planes : 0) + (bnb ? 1 : 0);
   const int res_stages =
       (aux_tiles > 0 && Cfg::kResSlots >= aux_tiles) ? Cfg::kResSlots / aux_tiles : 1;
 
@@ -141,7 +159,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_out);
     if (RES) tma_prefetch_desc(&tmap_res);
-    if (RES && p.bnb) tma_prefetch_desc(&tmap_z);
+    if (RES && bnb) tma_prefetch_desc(&tmap_z);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -166,6 +184,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above touched only this CTA's shared memory / TMEM.  From here on global memory
+  // written by the previous kernel of the stream is read: wait for it (no-op without PDL), then let
+  // the next kernel start its own prologue on SMs this grid leaves.
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -210,7 +233,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+      const uint32_t idesc =
+          p.f16 ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_bf16(kBlockM, BLOCK_N);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       if (WRES) mbar_wait(wfull_bar, 0);
@@ -249,16 +273,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int sb = 0; sb < kBlocksPerTile; ++sb) {
           const int col = n_blk * BLOCK_N + sb * 64;
           const bool res_here = has_res && col >= p.res_col_begin && col < p.res_col_begin + p.res_cols;
-          if (!res_here && !p.bnb) continue;
+          if (!res_here && !bnb) continue;
           const int n_res = res_here ? p.res_planes : 0;
           mbar_wait(rempty_bar + rs * 8, rphase ^ 1);
-          mbar_expect_tx(rfull_bar + rs * 8, (n_res + (p.bnb ? 1 : 0)) * Cfg::kTileBytes);
+          mbar_expect_tx(rfull_bar + rs * 8, (n_res + (bnb ? 1 : 0)) * Cfg::kTileBytes);
           const uint32_t slot0 = smem_res + rs * aux_tiles * Cfg::kTileBytes;
           for (int pl = 0; pl < n_res; ++pl)
             tma_load_4d(&tmap_res, rfull_bar + rs * 8, slot0 + pl * Cfg::kTileBytes,
                         col - p.res_col_begin + p.res_tma_col_off, row0 + p.res_tma_row_off, sample,
                         pl);
-          if (p.bnb)  // the Z tile always sits in the last slot of the stage
+          if (bnb)  // the Z tile always sits in the last slot of the stage
             tma_load_4d(&tmap_z, rfull_bar + rs * 8, slot0 + (aux_tiles - 1) * Cfg::kTileBytes, col,
                         row0, sample, 0);
           if (++rs == (uint32_t)res_stages) { rs = 0; rphase ^= 1; }
@@ -277,7 +301,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t ablock = 0;              // auxiliary stages seen so far
     const bool do_relu = p.flags & kEpiRelu;
     const bool do_res = p.flags & kEpiResidual;
-    const bool do_stats = p.flags & kEpiStats;
+    const bool do_stats = TRAIN && (p.flags & kEpiStats);
+    const bool f16 = p.f16 != 0;  // IEEE fp16 storage instead of bf16 (eval fp16 mode)
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
     const bool two_planes = OUT2 && p.out_planes == 2;
@@ -320,7 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int sb = 0; sb < kBlocksPerTile; ++sb, ++gblock) {
         const int cb = n_blk * BLOCK_N + sb * 64;  // first column of the store block
         const bool res_here = do_res && cb >= p.res_col_begin && cb < p.res_col_begin + p.res_cols;
-        const bool aux_here = RES && (res_here || p.bnb);
+        const bool aux_here = RES && (res_here || bnb);
         const uint32_t rs = aux_here ? ablock % (uint32_t)res_stages : 0u;
         const uint32_t ruse = aux_here ? ablock / (uint32_t)res_stages : 0u;  // n-th use of stage rs
         const uint32_t rphase = ruse & 1u;
@@ -365,8 +390,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int pl = 0; pl < p.res_planes; ++pl) {
                 const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4));
+                  if (f16) add_f16x8(v + q * 8, u); else add_bf16x8(v + q * 8, u);
+                }
               }
             }
           } else if (res_here && res_ok) {
@@ -376,7 +403,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (pl < p.res_planes) {
                 const uint4* r4 = reinterpret_cast<const uint4*>(rp + pl * p.res_plane_stride);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) add_bf16x8(v + q * 8, __ldg(r4 + q));
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = __ldg(r4 + q);
+                  if (f16) add_f16x8(v + q * 8, u); else add_bf16x8(v + q * 8, u);
+                }
               }
             }
           }
@@ -389,8 +419,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           } else {
             uint32_t hi[16];
+            if (f16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              for (int j = 0; j < 16; ++j) hi[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
             if (half == 0) {
               // This group's staging tile(s) must have been read out by the bulk store that used
               // them last (two store blocks ago).  The wait sits after the TMEM load and the math
@@ -427,7 +462,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
           }
-          if (RES && p.bnb) {
+          if (RES && bnb) {
             // dY = G(as stored) * dropmask/(1-p) * [Z*scale+shift > 0]; sums over this warp's 32 rows
             float zf[32];
 #pragma unroll
@@ -531,28 +566,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+// Programmatic dependent launch (on by default, VP3D_PDL=0 turns it off): the next kernel of the
+// stream may start its prologue (barrier init, TMEM allocation, descriptor prefetch) on SMs this
+// grid has already left; its griddepcontrol.wait still orders every global access behind the
+// completion of this grid.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VP3D_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN>;
+  // the dynamic shared memory opt-in is a per-device attribute
+  static bool attr_set[kMaxDevices] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
   const int total = m_tiles * args.n_tiles;
   if (total <= 0) return cudaSuccess;
   int grid = total < num_sms ? total : num_sms;
   if (WRES) grid = grid / args.n_tiles * args.n_tiles;  // a CTA keeps its N block for every tile
-  conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2>
-      <<<grid, 384, Cfg::kSmemBytes, stream>>>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(384, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
+}
+
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+static cudaError_t launch_train(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
+                                const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
+                                int num_sms, cudaStream_t stream) {
+  if ((args.flags & kEpiStats) || args.bnb)
+    return launch_impl<BLOCK_N, RES, WRES, OUT2, true>(a, w, o, r, z, args, num_sms, stream);
+  return launch_impl<BLOCK_N, RES, WRES, OUT2, false>(a, w, o, r, z, args, num_sms, stream);
 }
 
 template <int BLOCK_N, bool RES, bool WRES>
@@ -560,8 +630,8 @@ static cudaError_t launch_planes(const CUtensorMap& a, const CUtensorMap& w, con
                                  const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
                                  int num_sms, cudaStream_t stream) {
   if (args.out_planes == 2 && !(args.flags & kEpiOutF32))
-    return launch_impl<BLOCK_N, RES, WRES, true>(a, w, o, r, z, args, num_sms, stream);
-  return launch_impl<BLOCK_N, RES, WRES, false>(a, w, o, r, z, args, num_sms, stream);
+    return launch_train<BLOCK_N, RES, WRES, true>(a, w, o, r, z, args, num_sms, stream);
+  return launch_train<BLOCK_N, RES, WRES, false>(a, w, o, r, z, args, num_sms, stream);
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
@@ -581,7 +651,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
       if (res) {
         // (two output planes next to a TMA residual always run on 128-wide tiles, see run_conv)
         if (args.out_planes == 2) return cudaErrorInvalidConfiguration;
-        return launch_impl<256, true, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+        return launch_train<256, true, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
       }
       return launch_planes<256, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 128:

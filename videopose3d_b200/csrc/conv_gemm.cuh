@@ -27,6 +27,7 @@ namespace vp3d {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
+constexpr int kMaxDevices = 64;  // per-device caches (function attributes, SM counts)
 
 enum ConvGemmFlags : int {
   kEpiRelu = 1,        // y = max(y, 0)
@@ -49,6 +50,7 @@ struct ConvGemmArgs {
   int n_tiles;        // padded C_out / BLOCK_N
   int n_pad;          // padded C_out (rows per (plane, tap) slab of W)
   int pairs;          // 1 = bf16, 3 = bf16x3 (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo)
+  int f16;            // 1: operands, residual and 16-bit outputs are IEEE fp16 instead of bf16
   int flags;
   // ---- epilogue
   const float* scale;   // [n_pad] or null

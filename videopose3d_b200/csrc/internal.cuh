@@ -59,6 +59,7 @@ struct vp3d_plan {
   int nb = 0;  // residual blocks
   int C = 0, c_in_raw = 0, c_out_raw = 0, c_in_pad = 0, k0_pad = 0, c_out_pad = 0;
   int planes = 1;
+  int f16 = 0;  // VP3D_PRECISION_FP16: 16-bit stores hold IEEE fp16
   int pad[VP3D_MAX_WIDTHS];
   int shift_dil[VP3D_MAX_WIDTHS];  // causal shift in frames (TemporalModel, model.py:111)
   int shift_str[VP3D_MAX_WIDTHS];  // causal shift in strided units (Optimized1f, model.py:176)

@@ -1,5 +1,7 @@
 #include "pack.cuh"
 
+#include <cuda_fp16.h>
+
 #include <string.h>
 
 #include <stdint.h>
@@ -10,12 +12,19 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+// 16-bit storage of the fp16 eval mode: IEEE half bits in a bf16-typed slot (single plane),
+// saturating at +-65504 like the GEMM epilogue does.
+__device__ __forceinline__ __nv_bfloat16 f16_bits(float v) {
+  v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+  const unsigned short h = __half_as_ushort(__float2half_rn(v));
+  return __ushort_as_bfloat16(h);
+}
 
 // One thread per (row, 8-column group): 16-byte stores, coalesced along the row.
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                   int planes, int N, int T, int c_raw, int rows, int group,
                                   int frame_step, int k_pad, long long plane_stride,
-                                  const PackPerm perm) {
+                                  const PackPerm perm, int f16) {
   const int groups_per_row = k_pad >> 3;
   const long long total = (long long)N * rows * groups_per_row;
   const int k_valid = group * c_raw;
@@ -63,7 +72,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     for (int j = 0; j < 8; ++j) {
       const int k = g * 8 + j;
       const float v = (k < k_valid) ? __ldg(src + k) : 0.0f;
-      split_bf16(v, hi[j], lo[j]);
+      if (f16) hi[j] = f16_bits(v); else split_bf16(v, hi[j], lo[j]);
     }
     __nv_bfloat16* dst = out + row * k_pad + g * 8;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
@@ -73,7 +82,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
 
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
                               int c_raw, int rows, int group, int frame_step, int k_pad,
-                              long long plane_stride, cudaStream_t stream, const PackPerm* perm) {
+                              long long plane_stride, cudaStream_t stream, const PackPerm* perm,
+                              int f16) {
   PackPerm pp;
   memset(&pp, 0, sizeof(pp));
   if (perm) pp = *perm;
@@ -83,7 +93,7 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_input_kernel<<<(int)blocks, threads, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
-                                                         frame_step, k_pad, plane_stride, pp);
+                                                         frame_step, k_pad, plane_stride, pp, f16);
   return cudaGetLastError();
 }
 
@@ -91,7 +101,7 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
 // a warp cover one contiguous span of Conv1d.weight and each tap slab receives a coalesced bf16 row.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                         int planes, int c_out, int c_in, int taps, int n_pad,
-                                        int k_pad, int merged) {
+                                        int k_pad, int merged, int f16) {
   const long long slab = (long long)n_pad * k_pad;
   const long long plane_elems = (merged ? 1 : taps) * slab;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < slab;
@@ -105,7 +115,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
         v = __ldg(w + ((long long)co * c_in + ci) * taps + tap);
       }
       __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
+      if (f16) { hi = f16_bits(v); lo = hi; } else split_bf16(v, hi, lo);
       out[i] = hi;
       if (planes == 2) out[plane_elems + i] = lo;
     } else {
@@ -114,7 +124,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
       for (int tap = 0; tap < taps; ++tap) {
         const float v = in ? __ldg(src + tap) : 0.0f;
         __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
+        if (f16) { hi = f16_bits(v); lo = hi; } else split_bf16(v, hi, lo);
         out[tap * slab + i] = hi;
         if (planes == 2) out[plane_elems + tap * slab + i] = lo;
       }
@@ -124,13 +134,13 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
 
 cudaError_t launch_pack_conv_weight(const float* w, __nv_bfloat16* out, int planes, int c_out,
                                     int c_in, int taps, int n_pad, int k_pad, int merge_taps,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, int f16) {
   const long long total = (long long)n_pad * k_pad;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_conv_weight_kernel<<<(int)blocks, threads, 0, stream>>>(w, out, planes, c_out, c_in, taps,
-                                                               n_pad, k_pad, merge_taps);
+                                                               n_pad, k_pad, merge_taps, f16);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,8 @@ namespace vp3d {
 // the next strided conv are `w` contiguous row regions.  With block widths w_1..w_B and
 // R_i = N * rows_out(block i):  pos_0(n, t0) = (t0 mod w_1)*R_1 + pos_1(n, t0 / w_1), ...,
 // pos_B(n, t) = n*rows_out(B) + t.  `perm` carries (R_i, w_i) for i = 1..levels and rows_out(B).
+// f16 != 0 (both pack launchers): planes must be 1 and the 16-bit slots receive IEEE fp16 bits
+// (saturated at +-65504) instead of bf16 -- the operand format of the fp16 eval mode.
 struct PackPerm {
   int levels;        // number of residual blocks B (0 = natural order)
   int last_rows;     // rows per sample after the last block
@@ -27,7 +29,7 @@ struct PackPerm {
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, int N, int T,
                               int c_raw, int rows, int group, int frame_step, int k_pad,
                               long long plane_stride, cudaStream_t stream,
-                              const PackPerm* perm = nullptr);
+                              const PackPerm* perm = nullptr, int f16 = 0);
 
 // w: fp32 Conv1d weight (c_out, c_in, taps) (tap index innermost, model.py:102,113-118).
 // out: bf16 [planes][taps_out][n_pad][k_pad], zero padded.
@@ -35,7 +37,7 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
 //   merge_taps = 1: taps_out = 1,    out[pl][0][co][tap*c_in + ci] = w[co][ci][tap]
 cudaError_t launch_pack_conv_weight(const float* w, __nv_bfloat16* out, int planes, int c_out,
                                     int c_in, int taps, int n_pad, int k_pad, int merge_taps,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, int f16 = 0);
 
 // Eval-mode BatchNorm1d (model.py:32,117,119; eps = 1e-5) as y = x*scale + shift.
 // gamma/beta/mean/var: [c]; scale/shift: [c_pad] (padding: scale 0, shift 0).

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,6 +32,14 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -203,10 +212,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+// Same descriptor with IEEE fp16 operands (a/b format code 0 instead of 1), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// fp16 pair with saturation to +-65504 (an overflowing activation clamps instead of turning into inf
+// and poisoning every later layer with NaN)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu)));
+}
+__device__ __forceinline__ float f16_hi_to_f(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
 }
 __device__ __forceinline__ float bf16_lo_to_f(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi_to_f(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

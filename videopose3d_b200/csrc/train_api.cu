@@ -251,6 +251,8 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   if (N < 1) return fail(VP3D_ERR_INVALID, "forward_train: batch must be >= 1");
   if (dropout_p < 0.0f || dropout_p >= 1.0f)
     return fail(VP3D_ERR_INVALID, "forward_train: dropout p must be in [0, 1)");
+  if (p->f16)
+    return fail(VP3D_ERR_UNSUPPORTED, "forward_train: fp16 plans are inference-only");
   if (!p->conv_packed) return fail(VP3D_ERR_STATE, "forward_train: conv weights not packed");
   VP3D_TRY(ensure_train_state(p));
   TrainState* t = p->train;

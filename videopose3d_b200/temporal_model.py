@@ -10,6 +10,7 @@ There is no PyTorch/CPU execution path here: without the CUDA library or with CP
 ``forward`` raises.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -17,11 +18,48 @@ import torch.nn as nn
 from . import _capi
 
 _PRECISIONS = {"bf16": _capi.VP3D_PRECISION_BF16, "bf16x3": _capi.VP3D_PRECISION_BF16X3,
-               "mixed": _capi.VP3D_PRECISION_MIXED}
+               "mixed": _capi.VP3D_PRECISION_MIXED, "fp16": _capi.VP3D_PRECISION_FP16}
+
+
+class _PlanStore(dict):
+    """(device index, precision) -> plan handle.  Owns the handles: they are destroyed exactly once,
+    when the store itself is collected (weakref.finalize), never by a module that merely shares or
+    copies the reference.  Copies of a module start with an empty store of their own."""
+
+    def __init__(self):
+        super().__init__()
+        self._handles = []
+        self._finalizer = weakref.finalize(self, _PlanStore._destroy, self._handles)
+
+    def add(self, key, handle):
+        self[key] = handle
+        self._handles.append(handle)
+
+    def __deepcopy__(self, memo):
+        return _PlanStore()
+
+    def __copy__(self):
+        return _PlanStore()
+
+    def __reduce__(self):
+        return (_PlanStore, ())
+
+    @staticmethod
+    def _destroy(handles):
+        try:
+            lib = _capi.load()
+        except Exception:  # pragma: no cover - interpreter shutdown / library gone
+            return
+        for h in handles:
+            try:
+                lib.vp3d_plan_destroy(h)
+            except Exception:  # pragma: no cover
+                pass
+        del handles[:]
 
 
 def _default_precision():
-    p = os.environ.get("VP3D_PRECISION", "mixed")
+    p = os.environ.get("VP3D_PRECISION", "fp16")
     if p not in _PRECISIONS:
         raise ValueError(f"VP3D_PRECISION must be one of {sorted(_PRECISIONS)}, got {p!r}")
     return p
@@ -62,7 +100,7 @@ class TemporalModelBase(nn.Module):
         self._train_precision = os.environ.get("VP3D_TRAIN_PRECISION", "bf16")
         self._plan = None
         self._plan_key = None
-        self._plans = {}
+        self._plans = _PlanStore()
         self._packed = {}
         self._stats_epoch = 0      # bumped by every training forward (running stats changed)
         self._fwd_token = 0        # identifies the most recent training forward
@@ -137,9 +175,11 @@ class TemporalModelBase(nn.Module):
 
     # ------------------------------------------------------------------ engine controls
     def set_precision(self, precision):
-        """'mixed' (default: bf16 residual blocks, split-bf16 expand / shrink, exact residual
-        stream), 'bf16' (every GEMM plain bf16) or 'bf16x3' (every GEMM split-bf16,
-        fp32-faithful).  Not in the reference."""
+        """Eval-mode operand format.  'fp16' (default): IEEE fp16 operands and activations, fp32
+        accumulate -- ~4e-4 of the fp32 reference at the tensor rate of bf16; 'bf16x3': every GEMM
+        split-bf16 (fp32-faithful, ~1e-5); 'mixed': bf16 residual blocks on a hi+lo residual
+        stream, split-bf16 expand / shrink (~1e-3); 'bf16': every GEMM plain bf16 (~3e-3).  Not in
+        the reference."""
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         self._precision = precision
@@ -149,23 +189,64 @@ class TemporalModelBase(nn.Module):
     def precision(self):
         return self._precision
 
-    def _release_plan(self):
-        plans = getattr(self, "_plans", None)
-        if plans:
-            for handle in plans.values():
-                try:
-                    _capi.load().vp3d_plan_destroy(handle)
-                except Exception:  # pragma: no cover - interpreter shutdown
-                    pass
-        self._plans = {}
+    def _reset_engine_state(self):
+        """Forget every derived cache (plans, packed weights, workspace); the next forward rebuilds
+        them.  The plan handles themselves are released when their store is collected."""
+        self._plans = _PlanStore()
         self._packed = {}
         self._plan = None
+        self._plan_key = None
+        self._workspace = None
 
-    def __del__(self):
-        try:
-            self._release_plan()
-        except Exception:  # pragma: no cover
-            pass
+    def invalidate(self):
+        """Force a re-pack of every parameter on the next forward.  Needed only after edits that
+        bypass torch's version counters (``p.data.mul_()``, ``p.data.copy_()``, raw-pointer
+        writes): ordinary in-place ops, ``optimizer.step`` and ``load_state_dict`` are detected
+        automatically through ``tensor._version``.  Not in the reference."""
+        self._packed = {}
+        return self
+
+    # copies / replicas never share engine state with the original (the handles point into one
+    # device allocation each; sharing them made a collected copy free the original's plans)
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        import copy as _copy
+        skip = ("_plans", "_packed", "_plan", "_plan_key", "_workspace", "_grad_reducer")
+        for k, v in self.__dict__.items():
+            if k in skip:
+                continue
+            new.__dict__[k] = _copy.deepcopy(v, memo)
+        new._reset_engine_state()
+        new._grad_reducer = None
+        return new
+
+    def __copy__(self):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        new.__dict__.update(self.__dict__)
+        # nn.Module.__copy__-style shallow copy of the registries
+        for k in ("_parameters", "_buffers", "_modules"):
+            new.__dict__[k] = self.__dict__[k].copy()
+        new._reset_engine_state()
+        return new
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ("_plans", "_packed", "_plan", "_plan_key", "_workspace", "_grad_reducer"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_engine_state()
+        self._grad_reducer = None
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._reset_engine_state()
+        return replica
 
     def _config(self, precision):
         cfg = _capi.Config()
@@ -187,7 +268,9 @@ class TemporalModelBase(nn.Module):
     def _get_plan(self, device, precision=None):
         precision = precision or self._precision
         key = (device.index, precision)
-        plans = self.__dict__.setdefault("_plans", {})
+        plans = self.__dict__.get("_plans")
+        if plans is None:
+            plans = self._plans = _PlanStore()
         if key not in plans:
             lib = _capi.load()
             handle = _capi.ctypes.c_void_p()
@@ -195,7 +278,7 @@ class TemporalModelBase(nn.Module):
             with torch.cuda.device(device):
                 _capi.check(lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(handle)),
                             "vp3d_plan_create")
-            plans[key] = handle
+            plans.add(key, handle)
         self._plan = plans[key]
         self._plan_key = key
         return plans[key]
