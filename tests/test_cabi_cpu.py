@@ -219,3 +219,30 @@ def test_bone_length_penalty_matches_inline_reference_formula():
     assert torch.allclose(ours, ref, rtol=0, atol=0)
     ours.backward()
     assert pred.grad is not None and torch.isfinite(pred.grad).all()
+
+
+def test_copies_and_replicas_never_share_engine_state():
+    """copy / deepcopy / pickle / DataParallel replicas start with empty plan stores of their own
+    (a collected copy used to destroy the original's plans), and deepcopy works after a forward
+    has created ctypes handles (EMA / best-model patterns)."""
+    import copy
+    import pickle
+    from videopose3d_b200.temporal_model import _PlanStore
+    m = vp.TemporalModelOptimized1f(17, 2, 17, [3, 3], channels=64)
+    destroyed = []
+    m._plans._finalizer.detach()
+    m._plans = store = _PlanStore()
+    store._finalizer.detach()
+    store.add((0, "fp16"), _capi.ctypes.c_void_p(1234))   # what a first forward leaves behind
+    m._packed[((0, "fp16"), False)] = "versions"
+    clones = [copy.deepcopy(m), copy.copy(m), pickle.loads(pickle.dumps(m)),
+              m._replicate_for_data_parallel()]
+    for c in clones:
+        assert isinstance(c._plans, _PlanStore) and c._plans is not store and len(c._plans) == 0
+        assert c._packed == {} and c._plan is None
+        assert sorted(c.state_dict()) == sorted(m.state_dict())
+    assert torch.equal(clones[0].shrink.weight, m.shrink.weight)
+    assert clones[0].shrink.weight.data_ptr() != m.shrink.weight.data_ptr()
+    del clones
+    assert len(store) == 1 and destroyed == []             # the original still owns its plan
+    assert m.invalidate() is m and m._packed == {}

@@ -52,6 +52,19 @@ def _worker(rank, world, port, out):
             assert torch.allclose(flat[off:off + numel], exp, atol=1e-6), n
             assert flat[off:off + numel].view(params[n].shape).shape == params[n].shape
         assert red.launched == len(stage_spans)
+        # ragged last batch: rank r holds r + 1 of the 3 rows -> weights 1/3 and 2/3, not 1/2 each
+        red2 = GradientReducer(overlap=False)
+        red2.set_step_rows(rank + 1, 3)
+        v = torch.full((8,), float(rank + 1))
+        red2.reduce_flat(v)
+        assert torch.allclose(v, torch.full((8,), (1 * 1 + 2 * 2) / 3.0), atol=1e-6)
+        # bf16 wire format: same mean up to bf16 rounding of each contribution
+        red3 = GradientReducer(overlap=False, compress="bf16")
+        gr = torch.Generator().manual_seed(7 + rank)
+        w = torch.randn(1000, generator=gr)
+        exp = sum(torch.randn(1000, generator=torch.Generator().manual_seed(7 + r)) for r in range(world)) / world
+        red3.reduce_flat(w)
+        assert w.dtype == torch.float32 and float((w - exp).abs().max()) <= 2 ** -7
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()

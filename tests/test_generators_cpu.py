@@ -169,6 +169,32 @@ def test_ranks_partition_each_batch(host_emulation):
         assert np.array_equal(np.concatenate([_np(s[b][1]) for s in streams]), r3)
 
 
+def test_tail_batch_smaller_than_world_is_dropped_on_every_rank(host_emulation):
+    """len(pairs) % batch_size < world_size: the trailing batch cannot give every rank a row, so
+    all ranks skip it together (a rank entering the gradient all-reduce alone would hang)."""
+    rng = np.random.RandomState(3)
+    lens = [10, 9]                      # 19 windows, batch 8 -> batches of 8, 8, 3
+    p2 = [rng.uniform(-1, 1, (n, 17, 2)).astype(np.float32) for n in lens]
+    p3 = [rng.normal(0, 1, (n, 17, 3)).astype(np.float32) for n in lens]
+    world = 4
+    gens = [G.ChunkedGenerator(8, None, p3, p2, 1, pad=2, shuffle=True, random_seed=5, rank=r,
+                               world_size=world) for r in range(world)]
+    streams = [list(g.next_epoch()) for g in gens]
+    assert [len(s) for s in streams] == [2] * world            # the 3-row tail is gone everywhere
+    assert all(s[b][2].shape[0] == 2 for s in streams for b in range(2))
+    assert gens[0].last_shard == (2, 8)
+    # a tail that still feeds every rank is kept, with unequal shards reported for weighting
+    lens = [10, 11]                     # 21 windows -> 8, 8, 5
+    p2 = [rng.uniform(-1, 1, (n, 17, 2)).astype(np.float32) for n in lens]
+    p3 = [rng.normal(0, 1, (n, 17, 3)).astype(np.float32) for n in lens]
+    gens = [G.ChunkedGenerator(8, None, p3, p2, 1, pad=2, shuffle=False, rank=r, world_size=world)
+            for r in range(world)]
+    streams = [list(g.next_epoch()) for g in gens]
+    assert [len(s) for s in streams] == [3] * world
+    assert sorted(s[2][2].shape[0] for s in streams) == [1, 1, 1, 2]
+    assert sum(g.last_shard[0] for g in gens) == 5 and all(g.last_shard[1] == 5 for g in gens)
+
+
 def test_set_random_state_and_unchunked_toggle(host_emulation):
     cfg, cams, p3, p2, ref = load_generator_golden("gen_unchunked_aug")
     gen = G.UnchunkedGenerator(cams, p3, p2, **generator_kwargs(cfg))

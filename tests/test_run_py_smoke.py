@@ -18,7 +18,9 @@ import torch
 import videopose3d_b200 as vp
 from videopose3d_b200.optim import FusedAdam
 
-REFERENCE = "/root/reference"
+from oracle import stage_ref
+
+REFERENCE = stage_ref.reference_dir() or "/root/reference"   # staged archive on the GPU box
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "run.py")),

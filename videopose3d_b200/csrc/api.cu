@@ -97,15 +97,17 @@ int pick_block_n(int n_pad) {
   return 64;
 }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int cache[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return cache[dev];
 }
 
 // ------------------------------------------------------------------ operator level

@@ -193,13 +193,17 @@ template <int BLOCK_N>
 cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tmap_x,
                               const WgradArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = WCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+  // the dynamic shared memory opt-in is a per-device attribute
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
+    e = cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int total = a.taps * a.m_tiles * a.n_tiles * a.splits;
   if (total <= 0) return cudaSuccess;

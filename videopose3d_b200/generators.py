@@ -224,6 +224,7 @@ class ChunkedGenerator(_DeviceGeneratorBase):
         self.cameras, self.poses_3d, self.poses_2d = cameras, poses_3d, poses_2d
         self._rows_src = None
         self._rows_dev = None
+        self.last_shard = (0, 0)
 
     # -- reference API -------------------------------------------------------------------------
     @property
@@ -257,10 +258,18 @@ class ChunkedGenerator(_DeviceGeneratorBase):
             start, order = plan.begin()
             rows = self._device_rows(order)
             for b in range(start, plan.num_batches):
-                lo, hi = plan.batch_bounds(b)
-                lo, hi = shard_rows(lo, hi, self.rank, self.world_size)
+                g_lo, g_hi = plan.batch_bounds(b)
                 if plan.endless:
                     plan.state = (b + 1, order)
+                # A trailing batch with fewer rows than ranks would leave some ranks without work
+                # while the others enter the gradient all-reduce: every rank drops it (the decision
+                # depends only on (b, world_size), so it is the same everywhere).
+                if self.world_size > 1 and g_hi - g_lo < self.world_size:
+                    continue
+                lo, hi = shard_rows(g_lo, g_hi, self.rank, self.world_size)
+                # rows of this rank / of the whole batch: GradientReducer.set_step_rows() uses
+                # them to weight unequal shards (sum_r n_r/n * g_r instead of a plain mean)
+                self.last_shard = (hi - lo, g_hi - g_lo)
                 yield self._emit(rows, lo, hi - lo, self.chunk_length + 2 * self.pad,
                                  -self.pad - self.causal_shift, self.chunk_length)
             if not plan.endless:

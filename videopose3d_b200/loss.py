@@ -41,13 +41,14 @@ class _Mpjpe(torch.autograd.Function):
                                                loss.data_ptr(),
                                                dpred.data_ptr() if need_grad else None, stream),
                         "vp3d_mpjpe_fwd_bwd")
+        # kept for the lifetime of the graph: a second backward (retain_graph=True, or the loss
+        # feeding two backward passes) gets the same gradient again, as with the torch expression
         ctx.dpred = dpred
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         dpred = ctx.dpred
-        ctx.dpred = None
         return (dpred * grad_out if dpred is not None else None), None, None
 
 
@@ -96,7 +97,6 @@ class _ProjectedMpjpe(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         dpos, dtraj = ctx.grads
-        ctx.grads = None
         if dpos is None:
             return None, None, None, None, None
         return dpos * grad_out, dtraj * grad_out, None, None, None
