@@ -18,8 +18,16 @@ dominant kernel (block-1 3-tap conv GEMM, M = 27648, K = 3072, N = 1024) with CU
 own stream inside the timed steps; `cpu_baseline` times the oracle's torch.nn.functional port of
 the reference (what the reference executes on a host) on a bounded sample.
 
---impl reference: the reference's own CPU implementation of the same path (oracle port; the
-reference sources do not travel to the GPU box) on the host cores, same metric / config.
+Beside the headline the line carries `roofline_step` (executed FLOPs of the whole forward / step
+time / peak), `modes` (the other precision modes, short runs), and the training path: at N = 1 a
+`train` block for BASELINE configs[2] (TemporalModelOptimized1f, device-resident ChunkedGenerator
+-> forward + backward -> fused mpjpe -> FusedAdam, N = 1024), at N > 1 a `train_dp` block for
+configs[3] (the same step data-parallel: generator rows sharded by rank, one gradient all-reduce per
+step through data_parallel.GradientReducer over NCCL).
+
+--impl reference: the reference's own CPU implementation of the same path on the host cores, same
+metric / config: the UNMODIFIED reference classes from the archive staged by oracle/stage_ref.py
+(`cpu_baseline.kind` = "reference") or, if that is absent, the oracle port ("port").
 """
 import argparse
 import json
@@ -44,10 +52,41 @@ DOMINANT_LAUNCH_INDEX = 2             # pack_input, expand, [block-1 conv], ...
 DOMINANT_FLOPS_PER_LAUNCH = 2.0 * (N_PER_GPU * 27) * 3072 * 1024
 # its compulsory HBM bytes: A 27648x3072 bf16 + W 1024x3072 bf16 + out 27648x1024 bf16
 DOMINANT_ALGORITHMIC_BYTES = 2.0 * (N_PER_GPU * 27 * 3072 + 1024 * 3072 + N_PER_GPU * 27 * 1024)
-# DRAM bytes of that launch from the committed `ncu --set full` capture of the final build
-# (176.2 MB read + 34.6 MB written; below the algorithmic bytes because part of the freshly
-# written input is still L2-resident)
-DOMINANT_DRAM_BYTES_NCU = 210.8e6
+# DRAM bytes of that launch: read from the summary of an `ncu --set full` capture of THIS build
+# (profiles/traffic.json, written by tools/summarize_ncu_full.py --traffic; carries the sha256 of
+# the library it was captured from) -- null when no capture of the loaded library is committed.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+# training step (configs[2]): fwd 352.6 + dgrad 335.7 + wgrad 352.6 MFLOP/sample
+FLOPS_PER_SAMPLE_TRAIN = 1040.9e6
+WORKLOAD = ("TemporalModel arc=3,3,3,3,3 T=243 C=1024 J=17 eval forward, N=1024 windows per GPU "
+            "(BASELINE configs[1])")
+
+
+def lib_sha256():
+    import hashlib
+    from videopose3d_b200 import _capi
+    try:
+        with open(_capi.lib_path(), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()
+    except OSError:
+        return None
+
+
+def load_traffic(kernel_key):
+    """DRAM bytes per launch of `kernel_key` from the committed capture, with provenance."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, "no profiles/traffic.json"
+    ent = t.get("kernels", {}).get(kernel_key)
+    if not ent:
+        return None, f"{kernel_key} not in profiles/traffic.json"
+    same = t.get("lib_sha256") == lib_sha256()
+    src = (f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of this launch "
+           f"({t.get('source', '?')}); captured from library sha256 {str(t.get('lib_sha256'))[:12]} "
+           f"({'the library loaded now' if same else 'NOT the library loaded now'})")
+    return float(ent["dram_bytes"]), src
 
 
 def load_peaks():
@@ -57,6 +96,15 @@ def load_peaks():
             p = json.load(f)
         return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_sustained_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0
 
 
 class ClockSampler(threading.Thread):
@@ -130,6 +178,30 @@ def usable_cores():
     return max(1, n)
 
 
+def reference_model_module():
+    """`common.model` of the UNMODIFIED reference (/root/reference, or the archive staged by
+    oracle/stage_ref.py that travelled to this box), or None."""
+    try:
+        from oracle import stage_ref
+        return stage_ref.import_reference()
+    except Exception:
+        return None
+
+
+def make_cpu_reference(ref_mod):
+    """(callable x -> y, kind): the reference's own TemporalModel in eval mode on the CPU
+    ("reference"), else the oracle's torch.nn.functional port ("port").  Same seeded parameters."""
+    import torch
+    from oracle import temporal_model_oracle as orc
+    sd = orc.make_state_dict(J, F, J, ARC, C, seed=0)
+    if ref_mod is not None:
+        m = ref_mod.TemporalModel(J, F, J, filter_widths=ARC, causal=False, dropout=0.25, channels=C)
+        m.load_state_dict(sd)
+        m.eval()
+        return (lambda x: m(x)), "reference"
+    return (lambda x: orc.forward_torch(sd, x, ARC)), "port"
+
+
 def pick_cpu_threads():
     """The reference gets the thread count that serves it best: a short calibration of the same
     forward over {8, 16, 32, 64, all usable cores} threads, fastest wins."""
@@ -137,15 +209,15 @@ def pick_cpu_threads():
     from oracle import temporal_model_oracle as orc
     cores = usable_cores()
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores} | {cores})
-    sd = orc.make_state_dict(J, F, J, ARC, C, seed=0)
+    fwd, _ = make_cpu_reference(reference_model_module())
     x = orc.make_input(8, T, J, F, seed=1)
     best, best_dt = cands[-1], None
     with torch.no_grad():
         for c in cands:
             torch.set_num_threads(c)
-            orc.forward_torch(sd, x[:2], ARC)
+            fwd(x[:2])
             t0 = time.perf_counter()
-            orc.forward_torch(sd, x, ARC)
+            fwd(x)
             dt = time.perf_counter() - t0
             if best_dt is None or dt < best_dt:
                 best, best_dt = c, dt
@@ -153,21 +225,21 @@ def pick_cpu_threads():
 
 
 def cpu_reference_run(n_sample, reps, threads):
-    """Time the oracle's torch.nn.functional port of the reference TemporalModel (dense as written,
-    fp32, MKL-DNN) on the host.  Returns frames/s."""
+    """Time the reference TemporalModel (dense as written, fp32, MKL-DNN) on the host: the real
+    reference class when its archive is present, else the oracle port.  -> frames/s, s, kind."""
     import torch
     from oracle import temporal_model_oracle as orc
     torch.set_num_threads(threads)
-    sd = orc.make_state_dict(J, F, J, ARC, C, seed=0)
+    fwd, kind = make_cpu_reference(reference_model_module())
     x = orc.make_input(n_sample, T, J, F, seed=1)
     with torch.no_grad():
-        orc.forward_torch(sd, x[: max(1, n_sample // 8)], ARC)  # warm-up (thread pool, primitives)
+        fwd(x[: max(1, n_sample // 8)])  # warm-up (thread pool, primitives)
         t0 = time.perf_counter()
         for _ in range(reps):
-            y = orc.forward_torch(sd, x, ARC)
+            y = fwd(x)
         dt = time.perf_counter() - t0
     assert y.shape == (n_sample, 1, J, 3)
-    return n_sample * reps / dt, dt
+    return n_sample * reps / dt, dt, kind
 
 
 def cudnn_reference_arch(dev, x, our_value):
@@ -202,8 +274,15 @@ def cudnn_reference_arch(dev, x, our_value):
             return self.shrink(x).permute(0, 2, 1).reshape(n, -1, J, 3)
 
     torch.backends.cudnn.benchmark = True
-    ref = Ref().to(dev).eval()
-    out = {}
+    ref_mod = reference_model_module()
+    if ref_mod is not None:   # the reference's own class, unmodified
+        ref = ref_mod.TemporalModel(J, F, J, filter_widths=ARC, causal=False, dropout=0.25,
+                                    channels=C).to(dev).eval()
+        impl = "reference common/model.py TemporalModel (staged archive)"
+    else:
+        ref = Ref().to(dev).eval()
+        impl = "re-statement of the reference architecture (no staged reference on this box)"
+    out = {"implementation": impl}
     for name, autocast in (("fp32_tf32", False), ("bf16_autocast", True)):
         def run():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
@@ -220,6 +299,7 @@ def cudnn_reference_arch(dev, x, our_value):
         ms = e0.elapsed_time(e1) / 5
         out[name] = {"ms_per_step": ms, "frames_per_s": N_PER_GPU / ms * 1e3,
                      "speedup_of_value": our_value / (N_PER_GPU / ms * 1e3)}
+    out["target"] = "north_star: >= 20x the reference PyTorch/cuDNN TemporalModel frames/s on this GPU"
     del ref
     torch.cuda.empty_cache()
     return out
@@ -233,31 +313,187 @@ def run_reference(args, rank, world):
     from oracle import temporal_model_oracle as orc
     threads, cores = pick_cpu_threads()
     torch.set_num_threads(threads)
-    sd = orc.make_state_dict(J, F, J, ARC, C, seed=0)
+    fwd, kind = make_cpu_reference(reference_model_module())
     x = orc.make_input(n_sample, T, J, F, seed=1)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 3))):
-            orc.forward_torch(sd, x, ARC)
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            orc.forward_torch(sd, x, ARC)
+            fwd(x)
         dt = time.perf_counter() - t0
     value = n_sample * args.steps / dt
+    what = ("the reference's own common/model.py TemporalModel (unmodified, staged archive)"
+            if kind == "reference" else "oracle forward_torch port of the reference TemporalModel")
     sample = (f"{n_sample} windows of T=243 per step (bounded sample of the N=1024 batch; rows are "
-              f"independent), TemporalModel dense-as-written, fp32, torch CPU, {threads} threads "
+              f"independent), {what}, dense-as-written, fp32, torch CPU, {threads} threads "
               f"(best of a calibration over thread counts; {cores} usable cores)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
         "data": "synthetic",
-        "config": {"workload": "TemporalModel arc=3,3,3,3,3 T=243 C=1024 eval forward (BASELINE configs[1])",
-                   "batch_per_step": n_sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def synthetic_stream(n_seq, seed=0):
+    """H36M-shaped synthetic stream of SURVEY §8d cfg4: `n_seq` sequences of 1000-6000 frames,
+    17 joints, 2-D keypoints ~U(-1, 1) and 3-D joints ~N(0, 0.5^2) m, float32."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1000, 6001, size=n_seq)
+    p2 = [rng.uniform(-1, 1, (int(n), J, F)).astype(np.float32) for n in lens]
+    p3 = [rng.normal(0, 0.5, (int(n), J, 3)).astype(np.float32) for n in lens]
+    return lens, p2, p3
+
+
+def measure_train(dev, rank, world, steps, warmup, n_seq, compress=None):
+    """BASELINE configs[2] (world = 1) / configs[3] (world > 1): TemporalModelOptimized1f training
+    step exactly as run.py:401-420 drives it -- batch from the (device-resident) ChunkedGenerator,
+    root joint zeroed, forward, mpjpe, backward, Adam(amsgrad) -- with this repo's fused loss and
+    optimiser.  Data parallel: global batch 1024 x world rows, rows sharded by rank, one gradient
+    all-reduce per step (GradientReducer, overlapped with the backward).  Returns a dict."""
+    import torch
+    import torch.distributed as dist
+    import videopose3d_b200 as vp
+    from videopose3d_b200 import generators as G, loss as vloss
+    from videopose3d_b200.data_parallel import GradientReducer
+    from videopose3d_b200.optim import FusedAdam
+
+    lens, p2, p3 = synthetic_stream(n_seq, seed=0)
+    left, right = [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16]
+    gen = G.ChunkedGenerator(N_PER_GPU * world, None, p3, p2, 1, pad=121, causal_shift=0, shuffle=True,
+                             random_seed=1234, augment=True, kps_left=left, kps_right=right,
+                             joints_left=left, joints_right=right, endless=True, device=dev,
+                             rank=rank, world_size=world)
+    it = gen.next_epoch()
+    torch.manual_seed(0)   # identical initial parameters on every rank
+    model = vp.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, causal=False, dropout=0.25,
+                                        channels=C).to(dev).train()
+    opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
+    reducer = GradientReducer(overlap=True, compress=compress) if world > 1 else None
+
+    def step():
+        _, y3, x2 = next(it)
+        y3[:, :, 0] = 0                       # run.py:407
+        opt.zero_grad()
+        loss = vloss.mpjpe(model(x2), y3)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(n):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a, b in evs:
+            a.record()
+            loss = step()
+            b.record()
+            loss.item()                       # run.py:414 reads the loss every step
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        gpu_ms = sum(a.elapsed_time(b) for a, b in evs) / n
+        return gpu_ms, wall / n * 1e3, float(loss)
+
+    out = {}
+    if world > 1:
+        # the same step without the collective first (per-rank cost of the local work in THIS run)
+        for _ in range(max(3, warmup)):
+            step()
+        local_ms, local_wall_ms, _ = timed(steps)
+        reducer.attach(model)
+        out["local_step_ms_no_collective"] = local_ms
+    for _ in range(max(3, warmup)):
+        step()
+    launches_bwd = model.last_launch_count()
+    gpu_ms, wall_ms, last_loss = timed(steps)
+    if world > 1:
+        t = torch.tensor([gpu_ms, wall_ms, out["local_step_ms_no_collective"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gpu_ms, wall_ms, local_ms = (float(v) for v in t)
+        out["local_step_ms_no_collective"] = local_ms
+    peak_tf, _, _ = load_peaks()
+    sustained = load_sustained_peak()
+    tf = FLOPS_PER_SAMPLE_TRAIN * N_PER_GPU / (gpu_ms * 1e-3) / 1e12
+    out.update({
+        "workload": ("TemporalModelOptimized1f arc=3,3,3,3,3 C=1024 training step: device ChunkedGenerator "
+                     f"batch ({n_seq} sequences of 1000-6000 frames, pad 121, shuffle + flip augmentation) "
+                     "-> forward (BatchNorm batch statistics, dropout 0.25) -> fused mpjpe -> backward -> "
+                     "FusedAdam(amsgrad), N=1024 windows per GPU"
+                     + (" (BASELINE configs[2])" if world == 1 else
+                        f", global batch {N_PER_GPU * world} rows sharded over {world} ranks, one gradient "
+                        "all-reduce per step (BASELINE configs[3])")),
+        "ms_per_step": gpu_ms, "ms_per_step_wall_incl_loss_item": wall_ms,
+        "frames_per_s": N_PER_GPU * world / (gpu_ms * 1e-3),
+        "frames_per_s_wall": N_PER_GPU * world / (wall_ms * 1e-3),
+        "executed_tflops_per_s_per_gpu": tf,
+        "frac_of_bf16_peak_burst": tf / peak_tf, "frac_of_bf16_peak_sustained": tf / sustained,
+        "dtype": "bf16 operands, fp32 accumulate / statistics / master weights",
+        "steps": steps, "last_loss": last_loss, "h2d_bytes_per_step": 0,
+        "timing": "CUDA events per step (max over ranks); the step's working set (~1 GB) exceeds L2",
+    })
+    if world > 1:
+        grad_bytes = sum(p.numel() for p in model.parameters()) * (2 if compress == "bf16" else 4)
+        out.update({
+            "parallelism": f"dp{world}: rows of each global batch sharded by rank, per-GPU BatchNorm "
+                           "statistics, ONE gradient all-reduce per step (NCCL, staged slices on a side "
+                           "stream overlapping the remaining backward)",
+            "allreduce_bytes_per_step": grad_bytes, "allreduce_wire_dtype": compress or "fp32",
+            "allreduce_slices_per_step": reducer.launched // max(1, steps + max(3, warmup)),
+            "exposed_collective_ms": gpu_ms - out["local_step_ms_no_collective"],
+            "weak_scaling_efficiency_vs_local_step": out["local_step_ms_no_collective"] / gpu_ms,
+        })
+    del model, opt, gen
+    torch.cuda.empty_cache()
+    return out
+
+
+def cudnn_train_step(dev):
+    """The reference's TemporalModelOptimized1f training step on stock PyTorch/cuDNN on this GPU
+    (TF32 default and bf16 autocast), torch.optim.Adam(amsgrad), same shapes; time only."""
+    import torch
+    from oracle import temporal_model_oracle as orc
+    ref_mod = reference_model_module()
+    if ref_mod is None:
+        return {"unavailable": "no staged reference on this box"}
+    torch.backends.cudnn.benchmark = True
+    x = orc.make_input(N_PER_GPU, T, J, F, seed=3).to(dev)
+    y = torch.randn(N_PER_GPU, 1, J, 3, device=dev) * 0.3
+    out = {"implementation": "reference common/model.py TemporalModelOptimized1f (staged archive)"}
+    for name, autocast in (("fp32_tf32", False), ("bf16_autocast", True)):
+        m = ref_mod.TemporalModelOptimized1f(J, F, J, filter_widths=ARC, causal=False, dropout=0.25,
+                                             channels=C).to(dev).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
+
+        def step():
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                pred = m(x)
+            loss = torch.mean(torch.norm(pred.float() - y, dim=-1))
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms_per_step": ms, "frames_per_s": N_PER_GPU / ms * 1e3}
+        del m, opt
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args, rank, local_rank, world):
@@ -360,6 +596,41 @@ def run_ours(args, rank, local_rank, world):
         total_ms, e2e_s = float(t[0]), float(t[1])
         dist.barrier()
 
+    # ---------------- the other precision modes (short, rank 0 prints them; not the headline)
+    modes = {}
+    if world == 1 and not args.no_modes:
+        with torch.no_grad():
+            for prec in ("fp16", "bf16", "mixed", "bf16x3"):
+                if prec == args.precision:
+                    continue
+                model.set_precision(prec)
+                for i in range(3):
+                    model(xs[i % n_buf])
+                torch.cuda.synchronize()
+                evs = []
+                for i in range(10):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    model(xs[i % n_buf])
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+                m_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+                modes[prec] = {"ms_per_step": m_ms, "frames_per_s": N_PER_GPU / (m_ms * 1e-3)}
+            model.set_precision(args.precision)
+    del xs, flush
+    torch.cuda.empty_cache()
+
+    # ---------------- training path (configs[2] at N = 1, configs[3] data-parallel at N > 1)
+    train = None
+    if not args.no_train:
+        try:
+            train = measure_train(dev, rank, world, args.train_steps, 5, args.sequences,
+                                  compress=args.grad_wire)
+        except Exception as e:  # the headline must survive a failure of the side measurement
+            train = {"error": repr(e)[:300]}
+
     frames = N_PER_GPU * world * args.steps
     value = frames / (total_ms * 1e-3)
     e2e_value = N_PER_GPU * world * e2e_steps / e2e_s
@@ -368,15 +639,19 @@ def run_ours(args, rank, local_rank, world):
 
     line = None
     if rank == 0:
+        traffic, traffic_src = load_traffic("dominant_eval_" + args.precision)
+        step_tf = FLOPS_PER_SAMPLE_CONE * N_PER_GPU / (total_ms / args.steps * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads, cores = pick_cpu_threads()
             n_sample = 64
-            cpu_value, cpu_dt = cpu_reference_run(n_sample, 2, threads)
-            cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"2 x {n_sample} windows of T=243 ({cpu_dt:.1f} s), oracle forward_torch "
-                             f"(reference TemporalModel dense-as-written, fp32 torch CPU, {threads} "
-                             f"threads = best of a calibration; {cores} usable cores)"}
+            cpu_value, cpu_dt, cpu_kind = cpu_reference_run(n_sample, 2, threads)
+            cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": cpu_kind,
+                   "sample": f"2 x {n_sample} windows of T=243 ({cpu_dt:.1f} s), "
+                             + ("the reference's own TemporalModel (unmodified, staged archive)"
+                                if cpu_kind == "reference" else "oracle forward_torch port")
+                             + f", dense-as-written, fp32 torch CPU, {threads} "
+                             f"threads = best of a calibration; {cores} usable cores"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -386,14 +661,16 @@ def run_ours(args, rank, local_rank, world):
                       "mixed": "bf16 (residual blocks plain bf16 on a hi+lo residual stream; expand "
                                "and shrink split-bf16; fp32 accumulate)"}[args.precision],
             "data": "synthetic",
-            "config": {
-                "workload": "TemporalModel arc=3,3,3,3,3 T=243 C=1024 J=17 eval forward, N=1024 "
-                            "windows per GPU (BASELINE configs[1])",
-                "batch_per_gpu": N_PER_GPU, "receptive_field": 243, "parallelism": f"dp{world} (independent batches, no collective)",
+            "config": {"workload": WORKLOAD},
+            "config_detail": {
+                "batch_per_gpu": N_PER_GPU, "receptive_field": 243,
+                "parallelism": f"dp{world} (eval: independent batches per rank, no collective; the "
+                               "data-parallel training step with its gradient all-reduce is `train_dp`)",
                 "schedule": "eval dependency-cone (strided) schedule: 352.6 MFLOP/sample executed "
                             "vs 5217.8 MFLOP/sample dense-as-written",
                 "l2": "256 MiB memset between timed steps + 8 rotating 33.8 MB input buffers",
                 "timing": "CUDA events per step, summed; max over ranks",
+                "precision_mode": args.precision,
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": N_PER_GPU * T * J * F * 4,
@@ -408,13 +685,18 @@ def run_ours(args, rank, local_rank, world):
             "launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": DOMINANT_DRAM_BYTES_NCU,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "of this launch (profiles/r1l_ncu_full_eval_mixed.csv, ID 2)",
+                         "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes": DOMINANT_ALGORITHMIC_BYTES, "peak_source": peak_src,
                          "kernel": "conv_gemm_kernel<256> block-1 3-tap conv (M=27648,K=3072,N=1024)",
                          "flops_per_launch": DOMINANT_FLOPS_PER_LAUNCH, "ms_per_launch": dom_ms,
                          "launches_timed": cnt.value},
+            "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                              "frac": step_tf / peak_tf,
+                              "frac_of_sustained_peak": step_tf / load_sustained_peak(),
+                              "what": "executed FLOPs of the whole forward (352.6 MFLOP/sample x 1024) / "
+                                      "ms_per_step, per GPU; all launches of the step incl. input pack, "
+                                      "expand and shrink"},
             "executed_tflops_per_s": FLOPS_PER_SAMPLE_CONE * N_PER_GPU * world * args.steps / (total_ms * 1e-3) / 1e12,
             "dense_equivalent_tflops_per_s": FLOPS_PER_SAMPLE_DENSE * N_PER_GPU * world * args.steps / (total_ms * 1e-3) / 1e12,
             "wall_s_timed_region": t_wall,
@@ -422,14 +704,26 @@ def run_ours(args, rank, local_rank, world):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if modes:
+            line["modes"] = modes
+        if train is not None:
+            line["train" if world == 1 else "train_dp"] = train
         if world == 1 and not args.no_cudnn:
             # informational: the reference architecture executed by stock PyTorch/cuDNN on this same
             # GPU and batch (the number north_star asks to beat by >= 20x); not the driver's
             # reference arm, which is the CPU run of --impl reference
             try:
-                line["cudnn_same_gpu"] = cudnn_reference_arch(dev, xs[0], value)
+                x_ref = orc.make_input(N_PER_GPU, T, J, F, seed=100).to(dev)
+                line["cudnn_same_gpu"] = cudnn_reference_arch(dev, x_ref, value)
+                del x_ref
+                if isinstance(train, dict) and "ms_per_step" in train:
+                    ct = cudnn_train_step(dev)
+                    for k in ("fp32_tf32", "bf16_autocast"):
+                        if k in ct:
+                            ct[k]["speedup_of_train_step"] = ct[k]["ms_per_step"] / train["ms_per_step"]
+                    line["train"]["cudnn_same_gpu"] = ct
             except Exception as e:  # never let the side measurement break the bench line
-                line["cudnn_same_gpu"] = {"error": repr(e)[:200]}
+                line.setdefault("cudnn_same_gpu", {})["error"] = repr(e)[:200]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -638,9 +932,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cudnn", action="store_true",
                     help="skip the informational PyTorch/cuDNN measurement of the reference architecture")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
+    ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
+    ap.add_argument("--train-steps", type=int, default=30)
+    ap.add_argument("--grad-wire", default=None, choices=[None, "bf16"],
+                    help="wire dtype of the gradient all-reduce in the data-parallel training block")
     ap.add_argument("--input-pipeline", action="store_true",
                     help="measure the training input pipeline (device generator vs CPU port) instead")
-    ap.add_argument("--sequences", type=int, default=600)
+    ap.add_argument("--sequences", type=int, default=300)
     args = ap.parse_args()
     if args.input_pipeline:
         if args.steps == 200:
@@ -661,7 +960,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29531",
                os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--precision", args.precision]
+               "--warmup", str(args.warmup), "--precision", args.precision,
+               "--train-steps", str(args.train_steps), "--sequences", str(args.sequences)]
+        cmd += ["--no-train"] if args.no_train else []
+        cmd += ["--grad-wire", args.grad_wire] if args.grad_wire else []
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, local_rank, world)
 

@@ -20,7 +20,8 @@ def pytest_configure(config):
 def golden_names():
     """Model fixtures (tests/golden/make_golden.py)."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("gen_")]
+    # gen_*: generator fixtures; semi_* / big_*: tests/golden/make_semi_golden.py (own loaders)
+    return [n for n in names if not n.startswith(("gen_", "semi_", "big_"))]
 
 
 def generator_golden_names():

@@ -276,3 +276,145 @@ def test_training_loss_curve_tracks_fp32_reference(cuda_device):
     assert wo[-1] < 0.6 * wo[0] and centre[-1] < 0.6 * centre[0]      # both learn
     for w in range(1, len(wo)):
         assert abs(wo[w] - centre[w]) <= 3 * noise[w] + 0.08 * centre[w], (w, wo[w], centre[w], noise[w])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[2] shape (arc 3,3,3,3,3, C = 1024) against the real reference: fixture
+# tests/golden/big_opt_33333_c1024_train.npz (tests/golden/make_semi_golden.py) -- output, running
+# statistics and every parameter gradient (conv-weight gradients as a 4096-entry strided sample
+# plus L2 norm and sum) at N = 32.  SURVEY §8d gate G1: <= 1e-3 in the fp32-faithful mode.
+# ---------------------------------------------------------------------------------------------
+def _load_big():
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import temporal_model_oracle as orc
+    z = np.load(os.path.join(GOLDEN_DIR, "big_opt_33333_c1024_train.npz"))
+    meta = json.loads(str(z["meta"]))
+    sd = orc.make_state_dict(meta["J"], meta["F"], meta["Jout"], meta["fw"], meta["C"], seed=meta["seed"])
+    check = np.array([float(v.double().sum()) for k, v in sorted(sd.items())])
+    assert np.allclose(check, z["sd_check"], rtol=0, atol=1e-9), "seeded parameters differ from the fixture's"
+    x = orc.make_input(meta["N"], meta["T"], meta["J"], meta["F"], seed=meta["seed"] + 1)
+    return meta, sd, x, z
+
+
+def test_cfg3_shape_train_step_matches_reference(cuda_device):
+    meta, sd, x, z = _load_big()
+    m = _build(meta, sd, cuda_device, "bf16x3")
+    y = m(x.to(cuda_device))
+    assert _rel(y, z["y"]) <= 1e-3
+    (y * torch.from_numpy(z["gy"]).to(cuda_device)).sum().backward()
+    worst = {}
+    for k, prm in m.named_parameters():
+        g = prm.grad.reshape(-1)
+        idx = torch.from_numpy(z["gidx/" + k]).to(cuda_device)
+        ref = z["gval/" + k]
+        norm, total, gmax = z["gnorm/" + k]
+        # sampled entries against the tensor's own scale (its max |gradient|)
+        err = float(np.abs(g[idx].cpu().numpy().astype(np.float64) - ref).max() / gmax)
+        # and two whole-tensor functionals: L2 norm and sum (the sum relative to the norm scale)
+        n_err = abs(float(g.double().norm()) - norm) / norm
+        s_err = abs(float(g.double().sum()) - total) / (norm * np.sqrt(g.numel()))
+        worst[k] = max(err, n_err, s_err)
+    bad = {k: v for k, v in worst.items() if not v <= 1e-3}
+    print(f"cfg3-shape gradients vs reference: worst {max(worst.values()):.2e}")
+    assert not bad, f"gradient mismatch: {bad}"
+    sd_new = m.state_dict()
+    for k in z.files:
+        if not k.startswith("new/"):
+            continue
+        if k.endswith("num_batches_tracked"):
+            assert int(sd_new[k[4:]]) == int(z[k])
+        else:
+            assert _rel(sd_new[k[4:]], z[k]) <= 1e-3, k
+
+
+def test_cfg3_shape_default_bf16_training_is_close_and_reproducible(cuda_device):
+    """Default training kernels (bf16 operands) on the cfg3-shape fixture: output within 2e-2 of the
+    reference, every gradient within 5e-2 relative L2 on the stored samples, and two identical
+    steps give BIT-IDENTICAL gradients (batch statistics are reduced in a fixed order)."""
+    meta, sd, x, z = _load_big()
+    gy = torch.from_numpy(z["gy"]).to(cuda_device)
+    grads = []
+    for rep in range(2):
+        m = _build(meta, sd, cuda_device, "bf16")
+        y = m(x.to(cuda_device))
+        if rep == 0:
+            assert _rel(y, z["y"]) <= 2e-2
+        (y * gy).sum().backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    worst = {}
+    for k, g in grads[0].items():
+        idx = torch.from_numpy(z["gidx/" + k]).to(cuda_device)
+        ref = z["gval/" + k].astype(np.float64)
+        got = g.reshape(-1)[idx].cpu().numpy().astype(np.float64)
+        worst[k] = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+    print(f"cfg3-shape bf16 gradients vs fp32 reference (sample rel-L2): worst {max(worst.values()):.2e}")
+    assert max(worst.values()) <= 5e-2, worst
+    noise = max(float((grads[0][k] - grads[1][k]).norm() / grads[0][k].norm().clamp_min(1e-30)) for k in grads[0])
+    print(f"run-to-run gradient difference: {noise:.2e}")
+    assert noise <= 1e-3
+
+
+def test_dropout_keep_rate_scale_and_mask_consistency(cuda_device):
+    """SURVEY §8d gate G3 on the kernels' own output.  arc [3] (no residual block) with a shrink
+    layer that copies the first 51 channels makes the dropout output observable:
+    y[..., c] = drop(relu(bn(expand(x))))[..., c].  Against the same step with p = 0: every value is
+    either dropped (0) or scaled by exactly 1/(1-p) = 4/3; the kept fraction is 0.75 +- 3 sigma; and
+    the backward uses the same mask (d sum(y) / d beta_c = 4/3 x #kept positive rows)."""
+    C, J, N, T, p = 64, 17, 64, 50, 0.25
+    from oracle import temporal_model_oracle as orc
+    sd = orc.make_state_dict(J, 2, J, [3], C, seed=77)
+    sd["shrink.weight"] = torch.zeros(51, C, 1)
+    sd["shrink.weight"][torch.arange(51), torch.arange(51), 0] = 1.0
+    sd["shrink.bias"] = torch.zeros(51)
+    x = orc.make_input(N, T, J, 2, seed=78).to(cuda_device)
+    outs = {}
+    for prob in (0.0, p):
+        m = vp.TemporalModel(J, 2, J, filter_widths=[3], dropout=prob, channels=C)
+        m.load_state_dict(sd)
+        m = m.to(cuda_device).train().set_train_precision("bf16x3")
+        torch.manual_seed(5)
+        y = m(x)
+        y.sum().backward()
+        outs[prob] = (y.detach().reshape(-1, 51), m.expand_bn.bias.grad[:51].clone())
+    y0, _ = outs[0.0]
+    yp, dbeta = outs[p]
+    pos = y0 > 1e-4                                   # rows where ReLU passed a value
+    kept = pos & (yp != 0)
+    ratio = yp[kept] / y0[kept]
+    assert float((ratio - 4.0 / 3.0).abs().max()) <= 1e-3      # scale 1/(1-p), nothing in between
+    assert float(yp[~pos].abs().max()) <= 2e-4                 # dropout never creates values
+    n = int(pos.sum())
+    rate = float(kept.sum()) / n
+    sigma = (p * (1 - p) / n) ** 0.5
+    print(f"dropout keep rate {rate:.4f} over {n} activations (3 sigma = {3 * sigma:.4f})")
+    assert abs(rate - (1 - p)) <= 3 * sigma
+    # per-channel keep rates are unbiased too (no channel / row structure in the mask)
+    per_ch = kept.float().sum(0) / pos.float().sum(0).clamp_min(1)
+    assert float((per_ch - 0.75).abs().max()) <= 6 * (p * (1 - p) / (n / 51)) ** 0.5
+    # backward mask == forward mask: d sum(y)/d beta_c = 4/3 * (# kept activations of channel c
+    # with a positive pre-activation); dropped or negative rows contribute nothing
+    expect = kept.float().sum(0) * (4.0 / 3.0)
+    assert float((dbeta - expect).abs().max()) <= 1e-2 * float(expect.max())
+
+
+def test_total_causal_shift_and_receptive_field_match_reference(cuda_device):
+    """model.py:41-61 for both classes: the Python methods and the C-ABI entry points against values
+    produced by the real reference (tests/golden/causal_shift.json)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from videopose3d_b200 import _capi
+    rows = json.load(open(os.path.join(GOLDEN_DIR, "causal_shift.json")))
+    assert len(rows) >= 30
+    lib = _capi.load()
+    for r in rows:
+        cls = getattr(vp, r["cls"])
+        m = cls(17, 2, 17, filter_widths=r["arc"], causal=r["causal"], channels=64)
+        assert m.total_causal_shift() == r["total_causal_shift"], r
+        assert m.receptive_field() == r["receptive_field"], r
+        assert list(m.pad) == r["pad"] and list(m.causal_shift) == r["causal_shift"], r
+        plan = m.to(cuda_device)._get_plan(cuda_device)
+        assert lib.vp3d_total_causal_shift(plan) == r["total_causal_shift"], r
+        assert lib.vp3d_receptive_field(plan) == r["receptive_field"], r

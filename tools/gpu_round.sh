@@ -25,3 +25,8 @@ for f in ['bench','bench_nopdl','bench_bf16','bench_mixed','bench_bf16x3']:
         print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])
     except Exception as e: print(f, 'ERR', e)
 "
+# one `ncu --set full` capture of every launch of one eval forward (default mode) for profiles/
+sha256sum videopose3d_b200/_lib/libvp3d_b200.so | cut -d' ' -f1 > gpurun_out/${TAG}_lib_sha256.txt
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+  -o gpurun_out/${TAG}_full_eval_fp16 -f python tools/profile_steps.py eval fp16 > gpurun_out/${TAG}_full.log 2>&1
+ls -la gpurun_out | tail -20

@@ -315,6 +315,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int n_blk, sample, row0;
       tile_coords(p, tile, n_blk, sample, row0);
+      const int m_blk = tile / p.n_tiles;  // row-tile index: 4 slabs of 32 rows each
       const int t = row0 + r_in_tile;
       const bool valid = t < p.out_rows;
       const long long out_row = (long long)sample * p.out_rows + t;
@@ -472,7 +473,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               add_bf16x8(zf + q * 8, ld_shared_v4(zsrc + (((half * 4 + q) ^ sw) << 4)));
-            const int ch0 = c0 % p.bnb_c;
+            const int ch0 = c0 % p.bnb_c;   // channel of the layer below (columns repeat per tap)
             const bool drop = p.bnb_p > 0.0f;
             const uint32_t thresh = (uint32_t)(p.bnb_p * 65536.0f);
             const float inv_keep = drop ? 1.0f / (1.0f - p.bnb_p) : 1.0f;
@@ -516,8 +517,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
               }
             }
-            atomicAdd(p.bnb_sums + ch0 + lane, s[0]);
-            atomicAdd(p.bnb_sums + p.bnb_c + ch0 + lane, q2[0] * __ldg(p.bnb_invstd + ch0 + lane));
+            // per-slab partials (slab = 32 rows of this tile), summed in a fixed order by
+            // launch_ordered_col_sums: run-to-run reproducible, unlike atomics
+            float* bp = p.bnb_sums + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
+            bp[0] = s[0];
+            bp[p.n_pad] = q2[0];  // x invstd is applied after the ordered sum
           }
           if (RES && aux_here && half == 1)
             mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the auxiliary stage
@@ -544,8 +548,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
               }
             }
-            atomicAdd(p.stats + c0 + lane, s[0]);
-            atomicAdd(p.stats + p.n_pad + c0 + lane, q[0]);
+            // per-slab (32 rows) sum and sum of squares; bn_stats_finalize turns each slab into
+            // (count, mean, M2) and merges the slabs in a fixed order (Chan et al.): reproducible,
+            // and free of the E[x^2] - E[x]^2 cancellation over the whole batch
+            float* sp = p.stats + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
+            sp[0] = s[0];
+            sp[p.n_pad] = q[0];
           }
         }
       }

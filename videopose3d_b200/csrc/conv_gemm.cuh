@@ -81,7 +81,7 @@ struct ConvGemmArgs {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
-  float* bnb_sums;              // [2][bnb_c]
+  float* bnb_sums;              // partials [4 * row tiles][2][n_pad], see `stats`
   float bnb_p;                  // dropout probability of that layer (0 = none)
   unsigned bnb_seed_lo, bnb_seed_hi, bnb_layer;
   __nv_bfloat16* out;          // bf16 output plane 0, [samples*out_rows, out_ld]
@@ -91,7 +91,9 @@ struct ConvGemmArgs {
   float* out_f32;              // fp32 output [rows, out_f32_ld], only first n_valid columns
   int out_f32_ld;
   int n_valid;                 // number of real output channels (<= n_pad)
-  float* stats;                // [2][n_pad] running sum / sumsq accumulators (atomicAdd)
+  float* stats;                // partials [4 * row tiles][2][n_pad]: per 32-row slab of every row
+                               // tile the per-channel sum and sum of squares (plain stores, every
+                               // entry written; reduced in a fixed order afterwards)
   // two output planes: the lo plane is only produced for tiles that intersect rows
   // [lo_row_begin, lo_row_end) (flat tiling; the rows a later residual add / split-bf16 GEMM reads)
   int lo_row_begin, lo_row_end;
