@@ -226,16 +226,20 @@ typedef struct {
   float* out_f32;       /* fp32 [rows][out_f32_ld] (first n_valid channels) or NULL */
   int out_f32_ld;
   int n_valid;
-  float* stats;         /* [2][n_pad] sum / sum-of-squares accumulators or NULL */
+  float* stats;         /* NULL, or per-slab partials [4 * row tiles][2][n_pad]: for every 32-row slab of
+                         * every 128-row tile the per-channel sum and sum of squares of the stored
+                         * value (plain stores, every entry written, no atomics: reproducible) */
   /* fused BatchNorm-backward reductions (training data-gradient GEMMs, single-plane bf16 only):
    * bnb_z = pre-BN output Z of the layer whose activation gradient this GEMM produces, same
-   * [rows][out_ld] view as `out`; accumulates sum(dY) and invstd*sum(dY*(Z-mean)) into bnb_sums. */
+   * [rows][out_ld] view as `out`; writes slab partials of sum(dY) and sum(dY*(Z-mean)) to bnb_sums. */
   const void* bnb_z;    /* NULL = off */
   const float* bnb_scale;
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
-  float* bnb_sums;      /* [2][bnb_c] */
+  float* bnb_sums;      /* per-slab partials [4 * row tiles][2][n_pad] of sum(dY) and sum(dY*(Z-mean))
+                         * (summed in a fixed order, folded modulo bnb_c and scaled by invstd by the
+                         * caller; bnb_invstd is not read by the kernel) */
   int bnb_c;            /* channels of that layer (column index modulo bnb_c) */
   float bnb_p;          /* its dropout probability */
   unsigned long long bnb_seed;

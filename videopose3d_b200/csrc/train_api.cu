@@ -31,6 +31,8 @@ struct TrainState {
   float* vec = nullptr;       // per BN layer l: scale, shift, mean, invstd, stats[2C], sums[2C]
   size_t vec_floats = 0;
   float* shrink_affine = nullptr;  // scale / shift of the shrink bias [2 * c_out_pad]
+  float* red_scratch = nullptr;    // second-level scratch of the ordered reductions
+  unsigned* red_counter = nullptr; // their ticket counters (zeroed once, self-resetting)
   // configuration of the last forward (needed by backward)
   int N = 0, T = 0;
   int L[VP3D_MAX_WIDTHS] = {};
@@ -73,6 +75,11 @@ int ensure_train_state(vp3d_plan* p) {
   t->vec_floats = (size_t)(2 * p->nb + 1) * 8 * p->C;
   VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->vec), t->vec_floats * sizeof(float)));
   VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->shrink_affine), 2 * p->c_out_pad * sizeof(float)));
+  if (p->C > kReduceMaxChannels)
+    return fail(VP3D_ERR_UNSUPPORTED, "training supports at most %d channels", kReduceMaxChannels);
+  VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->red_scratch), kReduceScratchFloats * sizeof(float)));
+  VP3D_TRY(t_alloc(t, reinterpret_cast<void**>(&t->red_counter), kReduceCounters * sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(t->red_counter, 0, kReduceCounters * sizeof(unsigned)));
   return VP3D_OK;
 }
 
@@ -92,6 +99,8 @@ struct TrainLayout {
   size_t h[VP3D_MAX_WIDTHS] = {};       // h[i] = output of the first conv (post act) of block i
   size_t g0 = 0, g1 = 0, dz = 0, dyp = 0, partial = 0;
   size_t partial_bytes = 0;
+  size_t slab = 0;         // per-slab statistics partials of the GEMM epilogues (fp32)
+  size_t slab_floats = 0;
   size_t total = 0;
   long long rows[VP3D_MAX_WIDTHS] = {};  // rows[i] = N * L[i]
 };
@@ -130,6 +139,22 @@ TrainLayout train_layout(const vp3d_plan* p, int N, int T, const int* L) {
   if (!strided && p->cfg.filter_widths[0] > max_taps) max_taps = p->cfg.filter_widths[0];
   w.partial_bytes = (size_t)8 * max_taps * round_up(p->C, 128) * round_up((int)n_max, 64) * 4;
   w.partial = take(w.partial_bytes);
+  // slab partials [4 * row tiles][2][columns]: the widest producer is a GEMM over rows[i] rows with
+  // taps*C columns (strided data gradient) or N * tiles(L) row tiles with C columns (dilated)
+  {
+    size_t need = 0;
+    for (int i = 0; i <= p->nb; ++i) {
+      const size_t tiles = strided ? (size_t)(w.rows[i] + 127) / 128
+                                   : (size_t)N * ((L[i] + 127) / 128);
+      const size_t cols = (strided && i >= 1) ? (size_t)p->taps[i] * C : C;
+      const size_t f = tiles * 4 * 2 * cols;
+      need = f > need ? f : need;
+    }
+    const size_t bias_part = (size_t)((w.rows[p->nb] + 63) / 64) * (p->c_out_raw > 64 ? p->c_out_raw : 64);
+    need = bias_part > need ? bias_part : need;
+    w.slab_floats = need + 1024;
+    w.slab = take(w.slab_floats * sizeof(float));
+  }
   w.total = off + 1024;
   return w;
 }
@@ -276,7 +301,7 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   for (int i = 0; i <= p->nb; ++i) t->L[i] = L[i];
   int launches = 0;
 
-  CUDA_TRY(cudaMemsetAsync(t->vec, 0, t->vec_floats * sizeof(float), stream));
+  float* slab_part = reinterpret_cast<float*>(base + wl.slab);
   CUDA_TRY(launch_bias_affine(w->shrink_bias, t->shrink_affine, t->shrink_affine + p->c_out_pad,
                               p->c_out_raw, p->c_out_pad, stream));
   ++launches;
@@ -290,12 +315,21 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
     q.samples = 1;
     q.per_sample_tiles = 0;
   };
+  int stats_per_sample_rows = 0;  // rows per sample of the last stats-producing GEMM if it ran on
+                                  // per-sample tiles (dilated layout), else 0
   auto bn = [&](int layer, const float* const* bnp, long long rows, const __nv_bfloat16* z,
                 __nv_bfloat16* out, const __nv_bfloat16* res, long long res_plane, RowMap map) -> int {
     const LayerVec v = layer_vec(p, layer);
-    CUDA_TRY(launch_bn_finalize(v.stats, rows, bnp[0], bnp[1], const_cast<float*>(bnp[2]),
-                                const_cast<float*>(bnp[3]), bn_momentum[layer], 1e-5f, v.scale,
-                                v.shift, v.mean, v.invstd, C, stream));
+    // the GEMM that produced z left per-slab sums in slab_part; its row tiling: flat over all rows
+    // (strided model and every 1x1 conv) or per-sample tiles (dilated model's k-tap convs)
+    const int per_sample_rows = stats_per_sample_rows;
+    const int tps = per_sample_rows ? (per_sample_rows + 127) / 128 : 0;
+    const int slabs = per_sample_rows ? N * tps * 4 : (int)((rows + 127) / 128) * 4;
+    CUDA_TRY(launch_bn_stats_finalize(slab_part, slabs, per_sample_rows ? 1 : 0,
+                                      per_sample_rows ? per_sample_rows : (int)rows, tps, bnp[0],
+                                      bnp[1], const_cast<float*>(bnp[2]), const_cast<float*>(bnp[3]),
+                                      bn_momentum[layer], 1e-5f, v.scale, v.shift, v.mean, v.invstd,
+                                      C, t->red_scratch, t->red_counter, stream));
     CUDA_TRY(launch_bn_apply(z, rows * C, out, rows * C, pl, rows, C, v.scale, v.shift,
                              drop_cfg(t, layer), res, res_plane, map, stream));
     launches += 2;
@@ -320,7 +354,8 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   }
   ++launches;
   d.out = bf(wl.z[0]); d.out_plane_stride = wl.rows[0] * C; d.out_ld = C;
-  d.stats = layer_vec(p, 0).stats;
+  d.stats = slab_part;
+  stats_per_sample_rows = d.per_sample_tiles ? d.out_rows : 0;
   VP3D_TRY(run_conv(&d, stream));
   ++launches;
   VP3D_TRY(bn(0, w->expand_bn, wl.rows[0], bf(wl.z[0]), bf(wl.x[0]), nullptr, 0, no_map));
@@ -339,7 +374,8 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
       d.per_sample_tiles = 1; d.tap_row_step = p->dilation[i]; d.out_rows = L[i];
     }
     d.out = bf(wl.z[l1]); d.out_plane_stride = rows * C; d.out_ld = C;
-    d.stats = layer_vec(p, l1).stats;
+    d.stats = slab_part;
+    stats_per_sample_rows = d.per_sample_tiles ? d.out_rows : 0;
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     VP3D_TRY(bn(l1, w->layers_bn[2 * (i - 1)], rows, bf(wl.z[l1]), bf(wl.h[i]), nullptr, 0, no_map));
@@ -349,7 +385,8 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
     d.w = p->conv[2 * (i - 1) + 1].w; d.taps = 1; d.k_per_tap = C; d.n_pad = C;
     d.out_rows = (int)rows;
     d.out = bf(wl.z[l2]); d.out_plane_stride = rows * C; d.out_ld = C;
-    d.stats = layer_vec(p, l2).stats;
+    d.stats = slab_part;
+    stats_per_sample_rows = 0;
     VP3D_TRY(run_conv(&d, stream));
     ++launches;
     const RowMap rm = strided ? RowMap{0, 0, fw[i], fw[i] / 2 + p->shift_str[i]}
@@ -401,6 +438,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
   float* partial = reinterpret_cast<float*>(base + wl.partial);
+  float* slab_part = reinterpret_cast<float*>(base + wl.slab);
   if (!g->expand_conv_weight || !g->shrink_weight || !g->shrink_bias || !g->expand_bn[0] ||
       !g->expand_bn[1])
     return fail(VP3D_ERR_INVALID, "backward: missing gradient buffer");
@@ -424,13 +462,18 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   // the epilogue of the GEMM that produces the incoming gradient (fuse_bnb); otherwise a separate
   // pass over (G, Z) computes them.
   const bool fuse = (pl == 1);
+  // geometry of the slab partials the last fused GEMM left behind (consumed by the next bn_bwd)
+  int bnb_slabs = 0, bnb_ld = 0;
   auto fuse_bnb = [&](vp3d_conv_desc& q, int layer) {
     if (!fuse) return;
     const LayerVec v = layer_vec(p, layer);
     q.bnb_z = bf(wl.z[layer]);
     q.bnb_scale = v.scale; q.bnb_shift = v.shift; q.bnb_mean = v.mean; q.bnb_invstd = v.invstd;
-    q.bnb_sums = v.sums; q.bnb_c = C; q.bnb_p = t->dropout_p; q.bnb_seed = t->seed;
+    q.bnb_sums = slab_part; q.bnb_c = C; q.bnb_p = t->dropout_p; q.bnb_seed = t->seed;
     q.bnb_layer = layer;
+    const int tiles = (q.out_rows + 127) / 128;
+    bnb_slabs = (q.per_sample_tiles ? q.samples * tiles : tiles) * 4;
+    bnb_ld = q.n_pad;
   };
   // BN + ReLU + dropout backward of `layer`: (gin, z) -> dz (+ dgamma, dbeta)
   auto bn_bwd = [&](int layer, long long rows, const __nv_bfloat16* gin, const __nv_bfloat16* z,
@@ -439,7 +482,17 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     const DropoutCfg dc = drop_cfg(t, layer);
     if (!fuse) {
       CUDA_TRY(launch_bn_bwd_reduce(gin, rows * C, z, rows * C, pl, rows, C, v.scale, v.shift,
-                                    v.mean, v.invstd, dc, v.sums, stream));
+                                    v.mean, v.invstd, dc, slab_part, wl.slab_floats, v.sums,
+                                    t->red_scratch, t->red_counter, stream));
+      launches += 2;
+    } else {
+      // ordered sum of the slab partials the producing GEMM's epilogue wrote; column blocks of a
+      // strided data gradient (one per tap) fold onto the same channel
+      if ((size_t)bnb_slabs * 2 * bnb_ld > wl.slab_floats)
+        return fail(VP3D_ERR_WORKSPACE, "backward: slab partial buffer too small");
+      CUDA_TRY(launch_ordered_col_sums(slab_part, bnb_slabs, 2, bnb_ld, C, bnb_ld / C, nullptr,
+                                       v.invstd, v.sums, v.sums + C, t->red_scratch, t->red_counter,
+                                       stream));
       ++launches;
     }
     CUDA_TRY(launch_bn_bwd_apply(gin, rows * C, z, rows * C, bf(wl.dz), rows * C, pl, rows, C,
@@ -452,9 +505,9 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   // ---- shrink backward: y = X_nb * Wsh^T + b
   CUDA_TRY(launch_pack_input(dy, bf(wl.dyp), pl, 1, (int)rows_top, p->c_out_raw, (int)rows_top, 1, 1,
                              co128, rows_top * co128, stream));
-  CUDA_TRY(cudaMemsetAsync(g->shrink_bias, 0, p->c_out_raw * sizeof(float), stream));
-  CUDA_TRY(launch_col_sum_f32(dy, rows_top, p->c_out_raw, g->shrink_bias, stream));
-  launches += 2;
+  CUDA_TRY(launch_col_sum_f32(dy, rows_top, p->c_out_raw, slab_part, wl.slab_floats, g->shrink_bias,
+                              t->red_scratch, t->red_counter, stream));
+  launches += 3;
   {
     WgradCall c;
     c.dz = bf(wl.dyp); c.dz_ld = co128; c.x = bf(wl.x[p->nb]); c.x_ld = C; c.rows = rows_top;

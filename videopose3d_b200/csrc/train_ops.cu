@@ -61,28 +61,167 @@ __device__ __forceinline__ void dropout_keep8(const DropoutCfg& d, long long ele
   }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, long long n,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float momentum, float eps, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ mean,
-                                   float* __restrict__ invstd, int c) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  const double m = (double)stats[i] / (double)n;
-  double var = (double)stats[c + i] / (double)n - m * m;
+// ---------------------------------------------------------------------------------------------
+// Ordered (run-to-run reproducible) per-channel reductions over slab partials.
+// Grid = (channel groups of 32, S splits); 256 threads = 8 warps, lane = channel inside the group.
+// Warp w of split y walks the partials p = y*8 + w, y*8 + w + 8S, ... in ascending order; the 8
+// warps are then merged in warp order through shared memory; with S > 1 every block writes its
+// result to `scratch` and the block that arrives last (ticket counter) merges the S results in
+// split order and produces the output.  Nothing depends on timing, so a given shape always sums
+// in the same order.
+// ---------------------------------------------------------------------------------------------
+struct SlabGeom {     // rows covered by slab s of a conv GEMM's row tiling (4 slabs per 128-row tile)
+  int dilated;        // 1: per-sample tiles
+  int out_rows;       // dilated: rows per sample; flat: total rows
+  int tiles_per_sample;
+};
+__device__ __forceinline__ int slab_count(const SlabGeom& g, int s) {
+  int tile = s >> 2;
+  if (g.dilated) tile %= g.tiles_per_sample;
+  const int row0 = tile * 128 + (s & 3) * 32;
+  const int left = g.out_rows - row0;
+  return left <= 0 ? 0 : (left < 32 ? left : 32);
+}
+
+struct Moments { float n, mean, m2; };
+__device__ __forceinline__ void merge(Moments& a, const Moments& b) {  // Chan et al., ordered
+  if (b.n <= 0.0f) return;
+  if (a.n <= 0.0f) { a = b; return; }
+  const float n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  const float f = b.n / n;
+  a.mean = fmaf(d, f, a.mean);
+  a.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  a.n = n;
+}
+
+__device__ __forceinline__ bool last_block_of_group(unsigned* counter, int splits) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter + blockIdx.x, 1u);
+    is_last = (t == (unsigned)splits - 1u);
+    if (is_last) counter[blockIdx.x] = 0;   // self-resetting: ready for the next launch
+  }
+  __syncthreads();
+  return is_last;
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geom, int c,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         float momentum, float eps, float* __restrict__ scale,
+                         float* __restrict__ shift, float* __restrict__ mean_out,
+                         float* __restrict__ invstd, float* __restrict__ scratch,
+                         unsigned* __restrict__ counter) {
+  __shared__ float sm[8][3][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  const int S = gridDim.y;
+  Moments acc = {0.0f, 0.0f, 0.0f};
+  if (ch < c) {
+#pragma unroll 4
+    for (int s = blockIdx.y * 8 + w; s < slabs; s += 8 * S) {
+      const int cnt = slab_count(geom, s);
+      if (cnt == 0) continue;
+      const float sum = __ldg(part + ((size_t)s * 2) * c + ch);
+      const float sq = __ldg(part + ((size_t)s * 2 + 1) * c + ch);
+      Moments b;
+      b.n = (float)cnt;
+      b.mean = sum / b.n;
+      b.m2 = fmaxf(fmaf(-sum, b.mean, sq), 0.0f);   // sum (x - mean)^2 inside the 32-row slab
+      merge(acc, b);
+    }
+  }
+  sm[w][0][lane] = acc.n; sm[w][1][lane] = acc.mean; sm[w][2][lane] = acc.m2;
+  __syncthreads();
+  if (w == 0) {
+    acc = {sm[0][0][lane], sm[0][1][lane], sm[0][2][lane]};
+    for (int k = 1; k < 8; ++k) merge(acc, Moments{sm[k][0][lane], sm[k][1][lane], sm[k][2][lane]});
+    if (S > 1 && ch < c) {
+      float* o = scratch + ((size_t)blockIdx.y * 3) * c + ch;
+      o[0] = acc.n; o[c] = acc.mean; o[2 * (size_t)c] = acc.m2;
+    }
+  }
+  if (S > 1) {
+    if (!last_block_of_group(counter, S)) return;
+    if (w != 0) return;
+    acc = {0.0f, 0.0f, 0.0f};
+    if (ch < c)
+      for (int y = 0; y < S; ++y) {
+        const float* o = scratch + ((size_t)y * 3) * c + ch;
+        merge(acc, Moments{__ldcg(o), __ldcg(o + c), __ldcg(o + 2 * (size_t)c)});
+      }
+  } else if (w != 0) {
+    return;
+  }
+  if (ch >= c) return;
+  const double n = (double)acc.n;
+  const double m = (double)acc.mean;
+  double var = n > 0.0 ? (double)acc.m2 / n : 0.0;
   if (var < 0.0) var = 0.0;
   const float is = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[i] * is;
-  scale[i] = sc;
-  shift[i] = beta[i] - (float)m * sc;
-  mean[i] = (float)m;
-  invstd[i] = is;
+  const float sc = gamma[ch] * is;
+  scale[ch] = sc;
+  shift[ch] = beta[ch] - (float)m * sc;
+  mean_out[ch] = (float)m;
+  invstd[ch] = is;
   if (running_mean) {
-    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
-    running_mean[i] = (float)((1.0 - momentum) * running_mean[i] + momentum * m);
-    running_var[i] = (float)((1.0 - momentum) * running_var[i] + momentum * unbiased);
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * m);
+    running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unbiased);
   }
+}
+
+// out[st][ch] = mul_st[ch] * sum_p sum_f part[p][st][f * c + ch]   (st < nstat <= 2, f < folds):
+// plain sums of slab partials in a fixed order; `folds` > 1 folds column blocks that belong to the
+// same channel (the taps of a strided data-gradient GEMM).
+__global__ void __launch_bounds__(256)
+ordered_col_sums_kernel(const float* __restrict__ part, int n_part, int nstat, int ld, int c,
+                        int folds, const float* __restrict__ mul0, const float* __restrict__ mul1,
+                        float* __restrict__ out0, float* __restrict__ out1,
+                        float* __restrict__ scratch, unsigned* __restrict__ counter) {
+  __shared__ float sm[8][2][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  const int S = gridDim.y;
+  float a0 = 0.0f, a1 = 0.0f;
+  if (ch < c) {
+    for (int p = blockIdx.y * 8 + w; p < n_part; p += 8 * S) {
+      const float* row = part + (size_t)p * nstat * ld + ch;
+      for (int f = 0; f < folds; ++f) {
+        a0 += __ldg(row + (size_t)f * c);
+        if (nstat == 2) a1 += __ldg(row + ld + (size_t)f * c);
+      }
+    }
+  }
+  sm[w][0][lane] = a0; sm[w][1][lane] = a1;
+  __syncthreads();
+  if (w == 0) {
+    a0 = sm[0][0][lane]; a1 = sm[0][1][lane];
+    for (int k = 1; k < 8; ++k) { a0 += sm[k][0][lane]; a1 += sm[k][1][lane]; }
+    if (S > 1 && ch < c) {
+      scratch[((size_t)blockIdx.y * 2) * c + ch] = a0;
+      scratch[((size_t)blockIdx.y * 2 + 1) * c + ch] = a1;
+    }
+  }
+  if (S > 1) {
+    if (!last_block_of_group(counter, S)) return;
+    if (w != 0) return;
+    a0 = a1 = 0.0f;
+    if (ch < c)
+      for (int y = 0; y < S; ++y) {
+        a0 += __ldcg(scratch + ((size_t)y * 2) * c + ch);
+        a1 += __ldcg(scratch + ((size_t)y * 2 + 1) * c + ch);
+      }
+  } else if (w != 0) {
+    return;
+  }
+  if (ch >= c) return;
+  out0[ch] = mul0 ? a0 * mul0[ch] : a0;
+  if (nstat == 2) out1[ch] = mul1 ? a1 * mul1[ch] : a1;
 }
 
 __device__ __forceinline__ long long map_row(const RowMap& m, long long r) {
@@ -200,20 +339,19 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
       s2[j] += dy[j] * (zv[j] - mu[j]);  // invstd factored out of the sum
     }
   }
-  float is[8];
-  load_vec8(invstd + c0, is);
   const int width = tl.G * 8;  // channels covered by this block
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sm[0][rl * width + cg * 8 + j] = s1[j];
-    sm[1][rl * width + cg * 8 + j] = s2[j] * is[j];
+    sm[1][rl * width + cg * 8 + j] = s2[j];  // x invstd after the ordered sum
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * width; i += 256) {
     const int which = i / width, ch = i - which * width;
     float t = 0.0f;
     for (int l = 0; l < lanes; ++l) t += sm[which][l * width + ch];
-    atomicAdd(sums + which * c + blockIdx.x * width + ch, t);
+    // partials [blockIdx.y][2][c], reduced in a fixed order by launch_ordered_col_sums
+    sums[((size_t)blockIdx.y * 2 + which) * c + blockIdx.x * width + ch] = t;
   }
 }
 
@@ -274,7 +412,7 @@ __global__ void col_sum_f32_kernel(const float* __restrict__ x, long long rows, 
   for (int col = threadIdx.x; col < c; col += blockDim.x) {
     float s = 0.0f;
     for (long long r = r0; r < min(rows, r0 + 64); ++r) s += x[r * c + col];
-    atomicAdd(out + col, s);
+    out[(size_t)blockIdx.x * c + col] = s;   // partials [chunk][c], reduced in a fixed order
   }
 }
 
@@ -342,13 +480,36 @@ RowTiling row_tiling(long long rows, int c, dim3& grid) {
 
 }  // namespace
 
-cudaError_t launch_bn_finalize(const float* stats, long long n, const float* gamma, const float* beta,
-                               float* running_mean, float* running_var, float momentum, float eps,
-                               float* scale, float* shift, float* mean, float* invstd, int c,
-                               cudaStream_t stream) {
-  bn_finalize_kernel<<<(c + 255) / 256, 256, 0, stream>>>(stats, n, gamma, beta, running_mean,
-                                                          running_var, momentum, eps, scale, shift,
-                                                          mean, invstd, c);
+static int pick_splits(int n_part) {
+  int S = (n_part + 63) / 64;   // ~8 partials per warp
+  if (S < 1) S = 1;
+  if (S > kReduceMaxSplits) S = kReduceMaxSplits;
+  return S;
+}
+
+cudaError_t launch_bn_stats_finalize(const float* part, int slabs, int dilated, int out_rows,
+                                     int tiles_per_sample, const float* gamma, const float* beta,
+                                     float* running_mean, float* running_var, float momentum,
+                                     float eps, float* scale, float* shift, float* mean,
+                                     float* invstd, int c, float* scratch, unsigned* counter,
+                                     cudaStream_t stream) {
+  if (c > kReduceMaxChannels) return cudaErrorInvalidValue;
+  SlabGeom g = {dilated, out_rows, tiles_per_sample};
+  const dim3 grid((c + 31) / 32, pick_splits(slabs));
+  bn_stats_finalize_kernel<<<grid, 256, 0, stream>>>(part, slabs, g, c, gamma, beta, running_mean,
+                                                     running_var, momentum, eps, scale, shift, mean,
+                                                     invstd, scratch, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ordered_col_sums(const float* part, int n_part, int nstat, int ld, int c,
+                                    int folds, const float* mul0, const float* mul1, float* out0,
+                                    float* out1, float* scratch, unsigned* counter,
+                                    cudaStream_t stream) {
+  if (c > kReduceMaxChannels || nstat < 1 || nstat > 2) return cudaErrorInvalidValue;
+  const dim3 grid((c + 31) / 32, pick_splits(n_part));
+  ordered_col_sums_kernel<<<grid, 256, 0, stream>>>(part, n_part, nstat, ld, c, folds, mul0, mul1,
+                                                    out0, out1, scratch, counter);
   return cudaGetLastError();
 }
 
@@ -367,14 +528,19 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bflo
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
                                  long long z_plane, int planes, long long rows, int c,
                                  const float* scale, const float* shift, const float* mean,
-                                 const float* invstd, DropoutCfg drop, float* sums,
-                                 cudaStream_t stream) {
+                                 const float* invstd, DropoutCfg drop, float* partials,
+                                 size_t partial_floats, float* sums, float* scratch,
+                                 unsigned* counter, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   dim3 grid;
   const RowTiling tl = row_tiling(rows, c, grid);
+  if ((size_t)grid.y * 2 * c > partial_floats) return cudaErrorInvalidValue;
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
-                                                 shift, mean, invstd, drop, sums, tl);
-  return cudaGetLastError();
+                                                 shift, mean, invstd, drop, partials, tl);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_ordered_col_sums(partials, (int)grid.y, 2, c, c, 1, nullptr, invstd, sums, sums + c,
+                                 scratch, counter, stream);
 }
 
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
@@ -391,11 +557,17 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
   return cudaGetLastError();
 }
 
-cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* out,
+cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* partials,
+                               size_t partial_floats, float* out, float* scratch, unsigned* counter,
                                cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  col_sum_f32_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, stream>>>(x, rows, c, out);
-  return cudaGetLastError();
+  const unsigned chunks = (unsigned)((rows + 63) / 64);
+  if ((size_t)chunks * c > partial_floats) return cudaErrorInvalidValue;
+  col_sum_f32_kernel<<<chunks, 64, 0, stream>>>(x, rows, c, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_ordered_col_sums(partials, (int)chunks, 1, c, c, 1, nullptr, nullptr, out, nullptr,
+                                 scratch, counter, stream);
 }
 
 cudaError_t launch_pack_conv_weight_t(const float* w, __nv_bfloat16* out, int planes, int c_out,
