@@ -321,6 +321,35 @@ int vp3d_projected_mpjpe_fwd_bwd(const float* pos, const float* traj, const floa
                                  int32_t joints, int32_t linear, float* loss, float* dpos,
                                  float* dtraj, void* stream);
 
+/* The whole loss head of the semi-supervised step (run.py:350-390, BASELINE configs[4]) and its
+ * gradients in ONE cooperative launch:
+ *   losses[0] = mpjpe(pos[:n_labeled], target_3d with joint 0 zeroed)                 run.py:336, 352
+ *   losses[1] = weighted_mpjpe(traj[:n_labeled], target_3d[:, :, 0:1], 1 / z_root)    run.py:335, 358-360
+ *   losses[2] = mpjpe(project_to_2d(pos[n_labeled:] + traj[n_labeled:], cam), target_2d)
+ *               (common/camera.py:37-67, or :69-88 when `linear`)                     run.py:374-379
+ *   losses[3] = mean_bone |mean_labeled(len) - mean_unlabeled(len)|, len = mean over frames of
+ *               ||joint - parents[joint]||_2 (parents = dataset.skeleton().parents()) run.py:383-387
+ *   losses[4] = sum of the terms selected by `terms` (run.py:354, 361, 380, 388; --no-proj and
+ *               --no-bone-length clear VP3D_SEMI_PROJ / VP3D_SEMI_BONE); unselected terms are still
+ *               reported in losses[0..3] when their inputs are given but carry no gradient
+ * pos: [n_labeled + n_unlabeled][frames][joints][3]; traj: [...][frames][1][3]; target_3d:
+ * [n_labeled][frames][joints][3] as the generator yields it (joint 0 = global trajectory);
+ * cam: [n_unlabeled][9]; target_2d: [n_unlabeled][frames][joints][2]; parents: [joints] int32
+ * (device).  dpos / dtraj (shapes of pos / traj; both NULL or both set) receive d losses[4] / d pos,
+ * / d traj.  n_unlabeled = 0 drops the penalty.  target_3d / cam / target_2d may be NULL when the
+ * terms that read them are not selected.  `scratch`: device memory of
+ * vp3d_semi_loss_scratch_bytes() bytes.  joints <= 32. */
+#define VP3D_SEMI_POS 1
+#define VP3D_SEMI_TRAJ 2
+#define VP3D_SEMI_PROJ 4
+#define VP3D_SEMI_BONE 8
+size_t vp3d_semi_loss_scratch_bytes(void);
+int vp3d_semi_loss_fwd_bwd(const float* pos, const float* traj, const float* target_3d,
+                           const float* cam, const float* target_2d, const int32_t* parents,
+                           int64_t n_labeled, int64_t n_unlabeled, int32_t frames, int32_t joints,
+                           int32_t linear, int32_t terms, float* losses, float* dpos, float* dtraj,
+                           void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

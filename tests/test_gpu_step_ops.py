@@ -192,3 +192,106 @@ def test_projected_mpjpe_matches_reference_formula(cuda_device, linear):
     with torch.no_grad():
         assert abs(vloss.projected_mpjpe(pos, traj, cam, target, linear=linear).item() - ref.item()) \
             <= 2e-6 * abs(ref.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# Semi-supervised loss head (BASELINE configs[4]) against the golden produced by the REAL
+# reference: run.py:329-390 executed literally with common/loss.py, common/camera.py and the
+# Human3.6M skeleton (tests/golden/make_semi_golden.py -> semi_333_c64.npz).
+# ---------------------------------------------------------------------------------------------
+def _load_semi():
+    import json
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "semi_333_c64.npz"))
+    return json.loads(str(z["meta"])), z
+
+
+@pytest.mark.parametrize("tag,linear", [("full/", False), ("lin/", True)])
+def test_semi_supervised_loss_head_matches_real_reference(cuda_device, tag, linear):
+    """The fused kernel on the reference's own model outputs: every loss term and
+    d loss_total / d (both model outputs) as autograd computed them through loss.py / camera.py."""
+    meta, z = _load_semi()
+    dev = cuda_device
+    pad = meta["pad"]
+    pos = torch.from_numpy(z[tag + "pred_pos"]).to(dev).requires_grad_(True)
+    traj = torch.from_numpy(z[tag + "pred_traj"]).to(dev).requires_grad_(True)
+    in3 = torch.from_numpy(z["inputs_3d"]).to(dev)
+    cam = torch.from_numpy(z["cam_semi"]).to(dev)
+    tgt2 = torch.from_numpy(z["inputs_2d_semi"]).to(dev)[:, pad:-pad, :, :2].contiguous()  # run.py:368
+    total, terms = vloss.semi_supervised_loss(pos, traj, in3, cam, tgt2, meta["parents"],
+                                              linear_projection=linear)
+    total.backward()
+    ref = z[tag + "losses"]
+    got = terms.cpu().numpy()
+    print("loss terms", got, "reference", ref)
+    for i in range(5):
+        assert abs(got[i] - ref[i]) <= 5e-6 * abs(ref[i]) + 1e-7, (i, got, ref)
+    assert abs(total.item() - ref[4]) <= 5e-6 * ref[4]
+    for g, name in ((pos.grad, "d_pred_pos"), (traj.grad, "d_pred_traj")):
+        r = torch.from_numpy(z[tag + name]).to(dev)
+        assert _close(g, r, 2e-5, 1e-8), (name, float((g - r).abs().max()), float(r.abs().max()))
+    # unselected terms carry no gradient: --no-proj / --no-bone-length of run.py:380, 382
+    p2, t2 = pos.detach().clone().requires_grad_(True), traj.detach().clone().requires_grad_(True)
+    tot2, terms2 = vloss.semi_supervised_loss(p2, t2, in3, cam, tgt2, meta["parents"], linear_projection=linear,
+                                              no_proj=True, bone_length_term=False)
+    tot2.backward()
+    assert abs(tot2.item() - (ref[0] + ref[1])) <= 5e-6 * (ref[0] + ref[1])
+    assert abs(terms2[2].item() - ref[2]) <= 5e-6 * ref[2]          # still reported (run.py:377)
+    n_lab = meta["n_labeled"]
+    assert float(p2.grad[n_lab:].abs().max()) == 0.0 and float(t2.grad[n_lab:].abs().max()) == 0.0
+
+
+def test_bone_length_penalty_matches_reference_formula(cuda_device):
+    """run.py:383-387 restated with torch ops on the GPU vs the kernel (penalty term alone)."""
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randn(12, 3, 17, 3, generator=g).to(cuda_device)
+    parents = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15]   # h36m 17-joint skeleton
+    split = 7
+    a = pred.clone().requires_grad_(True)
+    dists = a[:, :, 1:] - a[:, :, parents[1:]]
+    lengths = torch.mean(torch.norm(dists, dim=3), dim=1)
+    ref = torch.mean(torch.abs(torch.mean(lengths[:split], dim=0) - torch.mean(lengths[split:], dim=0)))
+    ref.backward()
+    b = pred.clone().requires_grad_(True)
+    ours = vloss.bone_length_penalty(b, split, parents)
+    (2.0 * ours).backward()
+    assert abs(ours.item() - ref.item()) <= 5e-6 * ref.item()
+    assert _close(b.grad, 2.0 * a.grad, 2e-5, 1e-9)
+
+
+def test_semi_supervised_step_end_to_end_matches_real_reference(cuda_device):
+    """Both models (position J_out = 17, trajectory J_out = 1; run.py:238-246) in train mode through
+    the fp32-faithful kernels + the fused loss head: model outputs, loss terms and EVERY parameter
+    gradient of both models against the reference's autograd (<= 1e-3 of each tensor's scale)."""
+    import numpy as np
+    import videopose3d_b200 as vp
+    meta, z = _load_semi()
+    dev = cuda_device
+    arc, C, J, pad = meta["arc"], meta["C"], meta["J"], meta["pad"]
+    models = {}
+    for name, jout in (("pos", J), ("traj", 1)):
+        sd = {k[len(f"sd_{name}/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"sd_{name}/")}
+        m = vp.TemporalModelOptimized1f(J, 2, jout, filter_widths=arc, dropout=0.0, channels=C)
+        m.load_state_dict(sd)
+        models[name] = m.to(dev).train().set_train_precision("bf16x3")
+    x_cat = torch.cat((torch.from_numpy(z["inputs_2d"]), torch.from_numpy(z["inputs_2d_semi"]))).to(dev)
+    pos = models["pos"](x_cat)
+    traj = models["traj"](x_cat)
+    assert float((pos.detach().cpu() - torch.from_numpy(z["full/pred_pos"])).abs().max()) <= \
+        1e-3 * float(np.abs(z["full/pred_pos"]).max())
+    tgt2 = torch.from_numpy(z["inputs_2d_semi"]).to(dev)[:, pad:-pad, :, :2].contiguous()
+    total, terms = vloss.semi_supervised_loss(pos, traj, torch.from_numpy(z["inputs_3d"]).to(dev),
+                                              torch.from_numpy(z["cam_semi"]).to(dev), tgt2, meta["parents"])
+    total.backward()
+    ref = z["full/losses"]
+    assert abs(total.item() - ref[4]) <= 1e-3 * ref[4]
+    worst = {}
+    for name, m in models.items():
+        for k, prm in m.named_parameters():
+            r = z[f"full/grad_{name}/{k}"]
+            worst[f"{name}.{k}"] = float(np.abs(prm.grad.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-30))
+    print(f"semi-supervised step: worst parameter-gradient deviation {max(worst.values()):.2e}")
+    bad = {k: v for k, v in worst.items() if not v <= 1e-3}
+    assert not bad, bad
