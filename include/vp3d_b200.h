@@ -304,6 +304,17 @@ typedef struct vp3d_adam_tensor {
 int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step, double lr,
                    double beta1, double beta2, double eps, double weight_decay, void* stream);
 
+/* vp3d_adam_step for the parameters of a model with a training plan, fused with the bf16 re-pack
+ * of the conv weights: tensors whose `param` is one of w->layers_conv_weight[] /
+ * w->shrink_weight are updated by a kernel that writes the fresh value into the plan's forward
+ * [tap][co][ci] and transposed [tap][ci][co] bf16 packs in the same pass; all others (BatchNorm,
+ * bias, expand conv) go through the plain kernel.  After the call the plan's packs match the
+ * updated parameters: the next vp3d_forward_train needs no vp3d_set_weights(VP3D_PACK_CONV |
+ * VP3D_PACK_CONV_T).  Requires that the plan has run (or packed for) a training forward. */
+int vp3d_adam_step_packed(vp3d_plan* plan, const vp3d_weights* w, const vp3d_adam_tensor* tensors,
+                          int32_t n_tensors, int64_t step, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, void* stream);
+
 /* Mean per-joint position error and its gradient in one launch (common/loss.py:11-17 mpjpe, :19-25
  * weighted_mpjpe; used at run.py:359, 413): loss = mean_j w_j * ||pred_j - target_j||_2 over
  * `joints_total` vectors of `dims` components; dpred (same shape as pred, may be NULL) receives

@@ -295,3 +295,53 @@ def test_semi_supervised_step_end_to_end_matches_real_reference(cuda_device):
     print(f"semi-supervised step: worst parameter-gradient deviation {max(worst.values()):.2e}")
     bad = {k: v for k, v in worst.items() if not v <= 1e-3}
     assert not bad, bad
+
+
+def test_fused_adam_repack_keeps_packed_weights_current(cuda_device):
+    """the optimizer update that also writes the bf16 forward / transposed packs gives
+    bit-identical parameters, optimizer state and next-step outputs as the plain update followed by
+    the separate re-pack kernels, with fewer launches."""
+    import videopose3d_b200 as vp
+    from videopose3d_b200.optim import FusedAdam
+    from oracle import temporal_model_oracle as orc
+    arc, C, N = [3, 3, 3], 128, 48
+    sd = orc.make_state_dict(17, 2, 17, arc, C, seed=9)
+    xs = [orc.make_input(N, 27, 17, 2, seed=20 + i).to(cuda_device) for i in range(4)]
+    tgt = torch.randn(N, 1, 17, 3, generator=torch.Generator().manual_seed(3)).to(cuda_device) * 0.3
+    runs = {}
+    for fused in (False, True):
+        for prec in ("bf16", "bf16x3"):
+            m = vp.TemporalModelOptimized1f(17, 2, 17, filter_widths=arc, dropout=0.0, channels=C)
+            m.load_state_dict(sd)
+            m = m.to(cuda_device).train().set_train_precision(prec)
+            opt = FusedAdam(m.parameters(), lr=1e-3, amsgrad=True)
+            opt.fuse_repack = fused
+            outs, launches = [], []
+            for x in xs:
+                opt.zero_grad()
+                y = m(x)
+                vloss.mpjpe(y, tgt).backward()
+                opt.step()
+                outs.append(y.detach().clone())
+                launches.append(opt.last_launches)
+            runs[(fused, prec)] = (outs, {k: v.detach().clone() for k, v in m.state_dict().items()},
+                                   opt.state_dict(), launches)
+    for prec in ("bf16", "bf16x3"):
+        a, b = runs[(False, prec)], runs[(True, prec)]
+        for ya, yb in zip(a[0], b[0]):
+            assert torch.equal(ya, yb)                     # same packs -> same forward, bit for bit
+        for k in a[1]:
+            assert torch.equal(a[1][k], b[1][k]), k
+        for sa, sb in zip(a[2]["state"].values(), b[2]["state"].values()):
+            for key in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                assert torch.equal(sa[key], sb[key])
+        # step 1 runs before any training plan is packed? no: the forward packed it -> fused from
+        # the first step on: plain kernel + fused conv kernel + 2 tiny expand packs
+        assert a[3][-1] == 1 and b[3][-1] == 4, (a[3], b[3])
+    # the eval plan still re-packs from the fp32 masters after training (separate cache entry)
+    m.eval()
+    with torch.no_grad():
+        y_eval = m.set_precision("bf16x3")(xs[0])
+    sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    y_o = orc.forward_numpy(sd_now, xs[0].cpu().numpy(), arc, strided=True)
+    assert float((y_eval.cpu() - torch.from_numpy(y_o).float()).abs().max() / abs(y_o).max()) <= 1e-3

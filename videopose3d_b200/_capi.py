@@ -191,6 +191,10 @@ SIGNATURES = {
     "vp3d_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamTensor), ctypes.c_int32, ctypes.c_int64,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_void_p]),
+    "vp3d_adam_step_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Weights),
+                                             ctypes.POINTER(AdamTensor), ctypes.c_int32, ctypes.c_int64,
+                                             ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_double, ctypes.c_void_p]),
     "vp3d_projected_mpjpe_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                                     ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,

@@ -52,6 +52,18 @@ struct PackedConv {
 
 struct TrainState;  // train_api.cu
 
+// step_ops.cu: Adam / AMSGrad update of conv weights that also refreshes their bf16 packs
+struct AdamPackItem {
+  vp3d_adam_tensor t;
+  __nv_bfloat16* fwd;   // forward pack [planes][taps][fwd_n_pad][fwd_k_pad] or null
+  __nv_bfloat16* tr;    // transposed pack [planes][taps][tr_n_pad][tr_k_pad] or null
+  int c_out, c_in, taps;
+  int fwd_n_pad, fwd_k_pad, tr_n_pad, tr_k_pad;
+};
+int launch_adam_pack(const AdamPackItem* items, int n, int planes, int64_t step, double lr,
+                     double beta1, double beta2, double eps, double weight_decay,
+                     cudaStream_t stream);
+
 }  // namespace vp3d
 
 struct vp3d_plan {

@@ -81,6 +81,82 @@ adam_step_kernel(const __grid_constant__ AdamBatch batch, const AdamHyper h) {
   }
 }
 
+// ---- AMSGrad + bf16 re-pack of the conv weights in one pass ---------------------
+// The forward GEMMs read bf16 [plane][tap][co][ci] packs of Conv1d.weight (co, ci, tap) and the
+// data-gradient GEMMs the transposed [plane][tap][ci][co] packs.  Instead of re-reading the 68 MB of
+// fp32 masters after every optimizer step to refresh them (pack_conv_weight_t_kernel, 9 launches),
+// the optimizer update itself emits both packs: a block owns a 32 x 32 (co, ci) tile for every tap,
+// updates p / m / v / vmax in place (36 B per element, as the plain kernel) and writes the fresh
+// value through shared memory so that both packs receive coalesced 64-byte bf16 rows (+4 B per
+// element instead of +8 B and a second sweep).
+struct PackTensor {
+  vp3d_adam_tensor t;
+  __nv_bfloat16* fwd;      // [planes][taps][fwd_n_pad][fwd_k_pad]
+  __nv_bfloat16* tr;       // [planes][taps][tr_n_pad][tr_k_pad]  (rows = ci, cols = co)
+  int c_out, c_in, taps;
+  int fwd_n_pad, fwd_k_pad, tr_n_pad, tr_k_pad;
+  int first_block, tiles_ci;
+};
+constexpr int kMaxPackTensors = 16;
+struct PackBatch {
+  PackTensor t[kMaxPackTensors];
+  int n, planes;
+};
+
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(const __grid_constant__ PackBatch batch, const AdamHyper h) {
+  __shared__ float sm[32][33];
+  int ti = 0;
+  while (ti + 1 < batch.n && (int)blockIdx.x >= batch.t[ti + 1].first_block) ++ti;
+  const PackTensor& q = batch.t[ti];
+  const int tile = blockIdx.x - q.first_block;
+  const int co0 = (tile / q.tiles_ci) * 32, ci0 = (tile % q.tiles_ci) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool amsgrad = q.t.max_exp_avg_sq != nullptr;
+  const long long fwd_plane = (long long)q.taps * q.fwd_n_pad * q.fwd_k_pad;
+  const long long tr_plane = (long long)q.taps * q.tr_n_pad * q.tr_k_pad;
+  for (int tap = 0; tap < q.taps; ++tap) {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int co = co0 + j, ci = ci0 + tx;
+      float pv = 0.0f;
+      if (co < q.c_out && ci < q.c_in) {
+        const long long k = ((long long)co * q.c_in + ci) * q.taps + tap;
+        pv = q.t.param[k];
+        float m = q.t.exp_avg[k], v = q.t.exp_avg_sq[k];
+        float x = amsgrad ? q.t.max_exp_avg_sq[k] : 0.0f;
+        adam_update(pv, q.t.grad[k], m, v, x, amsgrad, h);
+        q.t.param[k] = pv;
+        q.t.exp_avg[k] = m;
+        q.t.exp_avg_sq[k] = v;
+        if (amsgrad) q.t.max_exp_avg_sq[k] = x;
+        if (q.fwd) {
+          const long long o = ((long long)tap * q.fwd_n_pad + co) * q.fwd_k_pad + ci;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(pv);
+          q.fwd[o] = hi;
+          if (batch.planes == 2) q.fwd[fwd_plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+        }
+      }
+      sm[j][tx] = pv;
+    }
+    __syncthreads();
+    if (q.tr) {
+#pragma unroll
+      for (int j = ty; j < 32; j += 8) {
+        const int ci = ci0 + j, co = co0 + tx;
+        if (ci < q.c_in && co < q.c_out) {
+          const float v = sm[tx][j];
+          const long long o = ((long long)tap * q.tr_n_pad + ci) * q.tr_k_pad + co;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+          q.tr[o] = hi;
+          if (batch.planes == 2) q.tr[tr_plane + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- MPJPE ------------------------------------------------------------------------------------
 
 constexpr int kLossThreads = 256;
@@ -210,10 +286,9 @@ projected_mpjpe_kernel(const float* __restrict__ pos, const float* __restrict__ 
 
 #define VP3D_EXPORT extern "C" __attribute__((visibility("default")))
 
-VP3D_EXPORT int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step,
-                               double lr, double beta1, double beta2, double eps,
-                               double weight_decay, void* stream) {
-  using namespace vp3d;
+namespace vp3d {
+static int adam_hyper(AdamHyper* h, const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step,
+                      double lr, double beta1, double beta2, double eps, double weight_decay) {
   if (n_tensors < 0 || (n_tensors > 0 && tensors == nullptr))
     return fail(VP3D_ERR_INVALID, "vp3d_adam_step: bad tensor list");
   if (step < 1) return fail(VP3D_ERR_INVALID, "vp3d_adam_step: step must be >= 1 (got %lld)",
@@ -225,14 +300,57 @@ VP3D_EXPORT int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensor
   // bias corrections in double on the host, as torch.optim.Adam computes them from python floats
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
+  h->one_minus_beta1 = (float)(1.0 - beta1);
+  h->beta2 = (float)beta2;
+  h->one_minus_beta2 = (float)(1.0 - beta2);
+  h->eps = (float)eps;
+  h->weight_decay = (float)weight_decay;
+  h->step_size = (float)(lr / bc1);
+  h->bc2_sqrt = (float)sqrt(bc2);
+  return VP3D_OK;
+}
+
+// One fused launch over the conv weights listed in `packs` (train_api.cu resolves the destinations).
+int launch_adam_pack(const AdamPackItem* items, int n, int planes, int64_t step, double lr,
+                     double beta1, double beta2, double eps, double weight_decay,
+                     cudaStream_t stream) {
+  if (n <= 0) return VP3D_OK;
+  if (n > kMaxPackTensors) return fail(VP3D_ERR_UNSUPPORTED, "adam_pack: too many conv tensors");
   AdamHyper h;
-  h.one_minus_beta1 = (float)(1.0 - beta1);
-  h.beta2 = (float)beta2;
-  h.one_minus_beta2 = (float)(1.0 - beta2);
-  h.eps = (float)eps;
-  h.weight_decay = (float)weight_decay;
-  h.step_size = (float)(lr / bc1);
-  h.bc2_sqrt = (float)sqrt(bc2);
+  vp3d_adam_tensor dummy;
+  VP3D_TRY(adam_hyper(&h, &dummy, 0, step, lr, beta1, beta2, eps, weight_decay));
+  PackBatch b;
+  b.n = 0;
+  b.planes = planes;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const AdamPackItem& it = items[i];
+    if (!it.t.param || !it.t.grad || !it.t.exp_avg || !it.t.exp_avg_sq)
+      return fail(VP3D_ERR_INVALID, "adam_pack: tensor %d has a null pointer", i);
+    if (it.t.numel != (int64_t)it.c_out * it.c_in * it.taps)
+      return fail(VP3D_ERR_INVALID, "adam_pack: tensor %d has %lld elements, expected %d x %d x %d", i,
+                  (long long)it.t.numel, it.c_out, it.c_in, it.taps);
+    PackTensor& q = b.t[b.n++];
+    q.t = it.t; q.fwd = it.fwd; q.tr = it.tr;
+    q.c_out = it.c_out; q.c_in = it.c_in; q.taps = it.taps;
+    q.fwd_n_pad = it.fwd_n_pad; q.fwd_k_pad = it.fwd_k_pad;
+    q.tr_n_pad = it.tr_n_pad; q.tr_k_pad = it.tr_k_pad;
+    q.first_block = blocks;
+    q.tiles_ci = (it.c_in + 31) / 32;
+    blocks += ((it.c_out + 31) / 32) * q.tiles_ci;
+  }
+  adam_pack_kernel<<<blocks, 256, 0, stream>>>(b, h);
+  CUDA_TRY(cudaGetLastError());
+  return VP3D_OK;
+}
+}  // namespace vp3d
+
+VP3D_EXPORT int vp3d_adam_step(const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step,
+                               double lr, double beta1, double beta2, double eps,
+                               double weight_decay, void* stream) {
+  using namespace vp3d;
+  AdamHyper h;
+  VP3D_TRY(adam_hyper(&h, tensors, n_tensors, step, lr, beta1, beta2, eps, weight_decay));
   for (int base = 0; base < n_tensors; base += VP3D_ADAM_MAX_TENSORS) {
     AdamBatch b;
     b.n = 0;

@@ -614,3 +614,63 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   p->last_launches = launches;
   return VP3D_OK;
 }
+
+// Optimizer step that keeps the packed bf16 weights of a training plan current:
+// conv weights named in `w` are updated by the fused update + re-pack kernel, everything else by the
+// plain single-launch kernel; afterwards the plan's forward and transposed packs are fresh, so the
+// next vp3d_forward_train needs no vp3d_set_weights.  Replaces `optimizer.step()` (run.py:396, 420)
+// AND the re-pack that used to follow it.
+VP3D_API int vp3d_adam_step_packed(vp3d_plan* p, const vp3d_weights* w,
+                                   const vp3d_adam_tensor* tensors, int32_t n_tensors, int64_t step,
+                                   double lr, double beta1, double beta2, double eps,
+                                   double weight_decay, void* stream_) {
+  if (!p || !w || (n_tensors > 0 && !tensors))
+    return fail(VP3D_ERR_INVALID, "adam_step_packed: null argument");
+  if (p->f16) return fail(VP3D_ERR_UNSUPPORTED, "adam_step_packed: fp16 plans are inference-only");
+  TrainState* t = p->train;
+  if (!t || !t->packed_t || !p->conv_packed)
+    return fail(VP3D_ERR_STATE, "adam_step_packed: the plan has no packed training weights yet "
+                "(run a training forward first)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  std::vector<vp3d_adam_tensor> plain;
+  std::vector<AdamPackItem> packed;
+  bool expand_seen = false;
+  for (int i = 0; i < n_tensors; ++i) {
+    const vp3d_adam_tensor& a = tensors[i];
+    AdamPackItem it;
+    memset(&it, 0, sizeof(it));
+    it.t = a;
+    bool is_conv = false;
+    for (int l = 0; l < 2 * p->nb && !is_conv; ++l) {
+      if (a.param != w->layers_conv_weight[l] || !a.param) continue;
+      const int taps = (l % 2 == 0) ? p->taps[l / 2 + 1] : 1;
+      it.fwd = p->conv[l].w; it.tr = t->conv_t[l];
+      it.c_out = p->C; it.c_in = p->C; it.taps = taps;
+      it.fwd_n_pad = p->C; it.fwd_k_pad = p->C; it.tr_n_pad = p->C; it.tr_k_pad = p->C;
+      is_conv = true;
+    }
+    if (!is_conv && a.param && a.param == w->shrink_weight) {
+      it.fwd = p->shrink.w; it.tr = t->shrink_t;
+      it.c_out = p->c_out_raw; it.c_in = p->C; it.taps = 1;
+      it.fwd_n_pad = p->c_out_pad; it.fwd_k_pad = p->C;
+      it.tr_n_pad = p->C; it.tr_k_pad = c_out_pad128(p);
+      is_conv = true;
+    }
+    if (is_conv) packed.push_back(it);
+    else plain.push_back(a);
+    if (a.param && a.param == w->expand_conv_weight) expand_seen = true;
+  }
+  VP3D_TRY(vp3d_adam_step(plain.data(), (int32_t)plain.size(), step, lr, beta1, beta2, eps,
+                          weight_decay, stream_));
+  VP3D_TRY(launch_adam_pack(packed.data(), (int)packed.size(), p->planes, step, lr, beta1, beta2, eps,
+                            weight_decay, stream));
+  if (expand_seen) {  // 104 k elements: the two expand packs (dilated / tap-merged) the usual way
+    const int w0 = p->cfg.filter_widths[0];
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->C,
+                                     p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream));
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
+                                     p->c_in_raw, w0, p->C, p->k0_pad, 1, stream));
+  }
+  p->last_launches = (plain.empty() ? 0 : 1) + (packed.empty() ? 0 : 1) + (expand_seen ? 2 : 0);
+  return VP3D_OK;
+}

@@ -11,12 +11,21 @@ checkpoints written by either optimiser load into the other (run.py:295-296, 600
 reads p, g, m, v, vmax and writes p, m, v, vmax once (36 B per element) instead of the eight
 multi-tensor launches of torch's implementation.  CUDA float32 contiguous tensors only; anything
 else raises -- there is no fallback path.
+
+The bf16 re-pack of the conv weights is fused into the update: parameters that belong to a
+`TemporalModel*` of this package (found automatically; `attach(model)` registers one explicitly)
+go through `vp3d_adam_step_packed`, whose kernel writes the updated value straight into the
+forward and transposed bf16 packs of the model's training plan, so the next training forward finds
+them current (no pack kernels, no second read of the fp32 masters).  `fuse_repack = False` restores
+the plain update + separate re-pack.
 """
 import ctypes
+import weakref
 
 import torch
 
 from . import _capi
+from . import temporal_model as _tm
 
 __all__ = ["FusedAdam"]
 
@@ -35,6 +44,17 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError(f"Invalid weight_decay value: {weight_decay}")
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         super().__init__(params, defaults)
+        self._owners = {}     # id(param) -> weakref(model) for explicitly attached models
+        self.fuse_repack = True   # parameters of TemporalModel* instances are found automatically
+        self.last_launches = 0
+
+    def attach(self, *models):
+        """Fuse the conv-weight re-pack of these models into `step()` (see module docstring)."""
+        for m in models:
+            ref = weakref.ref(m)
+            for prm in m.parameters():
+                self._owners[id(prm)] = ref
+        return self
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -81,25 +101,50 @@ class FusedAdam(torch.optim.Optimizer):
                     self._check(st[key], key)
                 st["step"] += 1
                 by_step.setdefault(int(st["step"].item()), []).append((p, st))
+            self.last_launches = 0
             for step, items in by_step.items():
                 dev = items[0][0].device
                 if any(p.device != dev for p, _ in items):
                     raise RuntimeError("FusedAdam: parameters of one group must share a device")
-                table = (_capi.AdamTensor * len(items))()
-                for row, (p, st) in zip(table, items):
-                    row.param = p.data_ptr()
-                    row.grad = p.grad.data_ptr()
-                    row.exp_avg = st["exp_avg"].data_ptr()
-                    row.exp_avg_sq = st["exp_avg_sq"].data_ptr()
-                    row.max_exp_avg_sq = st["max_exp_avg_sq"].data_ptr() if group["amsgrad"] else None
-                    row.numel = p.numel()
+                # parameters of attached models whose training plan already holds packed weights go
+                # through the fused update + re-pack entry, model by model; the rest the plain way
+                by_model, plain = {}, []
+                for p, st in items:
+                    ref = self._owners.get(id(p))
+                    m = ref() if ref is not None else _tm.owner_of(p)
+                    if m is not None and self.fuse_repack and m._train_plan_ready(dev):
+                        by_model.setdefault(id(m), (m, []))[1].append((p, st))
+                    else:
+                        plain.append((p, st))
+
+                def table_of(rows):
+                    table = (_capi.AdamTensor * len(rows))()
+                    for row, (p, st) in zip(table, rows):
+                        row.param = p.data_ptr()
+                        row.grad = p.grad.data_ptr()
+                        row.exp_avg = st["exp_avg"].data_ptr()
+                        row.exp_avg_sq = st["exp_avg_sq"].data_ptr()
+                        row.max_exp_avg_sq = st["max_exp_avg_sq"].data_ptr() if group["amsgrad"] else None
+                        row.numel = p.numel()
+                    return table
+                hyper = (step, float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
+                         float(group["weight_decay"]))
                 with torch.cuda.device(dev):
                     stream = torch.cuda.current_stream(dev).cuda_stream
-                    _capi.check(lib.vp3d_adam_step(table, len(items), step, float(group["lr"]),
-                                                   float(beta1), float(beta2), float(group["eps"]),
-                                                   float(group["weight_decay"]), stream),
-                                "vp3d_adam_step")
+                    if plain:
+                        _capi.check(lib.vp3d_adam_step(table_of(plain), len(plain), *hyper, stream),
+                                    "vp3d_adam_step")
+                        self.last_launches += 1
+                    for m, rows in by_model.values():
+                        plan = m._get_plan(dev, m._train_precision)
+                        w = m._weights_struct()
+                        _capi.check(lib.vp3d_adam_step_packed(plan, ctypes.byref(w), table_of(rows),
+                                                              len(rows), *hyper, stream),
+                                    "vp3d_adam_step_packed")
+                        self.last_launches += lib.vp3d_last_launch_count(plan)
                 for p, _ in items:
                     # the kernel wrote through raw pointers: tell autograd / the weight-pack cache
                     torch.autograd.graph.increment_version(p)
+                for m, _ in by_model.values():
+                    m._mark_train_packs_current(dev)   # after the version bumps above
         return loss

@@ -21,6 +21,21 @@ _PRECISIONS = {"bf16": _capi.VP3D_PRECISION_BF16, "bf16x3": _capi.VP3D_PRECISION
                "mixed": _capi.VP3D_PRECISION_MIXED, "fp16": _capi.VP3D_PRECISION_FP16}
 
 
+# id(parameter) -> weakref(owning model): lets optim.FusedAdam find the model whose packed bf16
+# weights it can refresh while it updates the parameter (no API change for run.py, which builds the
+# optimizer from `model.parameters()` alone)
+_PARAM_OWNER = {}
+
+
+def owner_of(param):
+    """The live TemporalModel* that owns `param`, or None."""
+    ref = _PARAM_OWNER.get(id(param))
+    m = ref() if ref is not None else None
+    if m is None or not any(param is q for q in m.parameters()):
+        return None
+    return m
+
+
 class _PlanStore(dict):
     """(device index, precision) -> plan handle.  Owns the handles: they are destroyed exactly once,
     when the store itself is collected (weakref.finalize), never by a module that merely shares or
@@ -145,6 +160,12 @@ class TemporalModelBase(nn.Module):
             dilation *= w
         self.layers_conv = nn.ModuleList(convs)
         self.layers_bn = nn.ModuleList(bns)
+        self._register_params()
+
+    def _register_params(self):
+        ref = weakref.ref(self)
+        for prm in self.parameters():
+            _PARAM_OWNER[id(prm)] = ref
 
     # ------------------------------------------------------------------ reference API
     def set_bn_momentum(self, momentum):
@@ -220,6 +241,7 @@ class TemporalModelBase(nn.Module):
             new.__dict__[k] = _copy.deepcopy(v, memo)
         new._reset_engine_state()
         new._grad_reducer = None
+        new._register_params()
         return new
 
     def __copy__(self):
@@ -242,6 +264,7 @@ class TemporalModelBase(nn.Module):
         super().__setstate__(state)
         self._reset_engine_state()
         self._grad_reducer = None
+        self._register_params()
 
     def _replicate_for_data_parallel(self):
         replica = super()._replicate_for_data_parallel()
@@ -334,6 +357,21 @@ class TemporalModelBase(nn.Module):
         _capi.check(_capi.load().vp3d_set_weights(plan, _capi.ctypes.byref(w), what, stream),
                     "vp3d_set_weights")
         packed[key] = versions
+
+    # -- hooks for optim.FusedAdam.attach (update + re-pack in one kernel) ---------------------------
+    def _train_plan_ready(self, device):
+        """True when the training plan on `device` already holds packed weights (i.e. a training
+        forward has run): only then can the fused optimizer keep them current."""
+        key = ((device.index, self._train_precision), True)
+        return self.__dict__.get("_packed", {}).get(key) is not None
+
+    def _mark_train_packs_current(self, device):
+        """The fused optimizer step has just re-packed every conv weight of the training plan:
+        record the parameters' new versions so that the next forward does not pack again."""
+        conv, bn = self._param_tensors()
+        versions = (tuple((t.data_ptr(), t._version) for t in conv),
+                    tuple((t.data_ptr(), t._version) for t in bn) + (self._stats_epoch,))
+        self._packed[((device.index, self._train_precision), True)] = versions
 
     def _get_workspace(self, nbytes, device):
         ws = self._workspace
