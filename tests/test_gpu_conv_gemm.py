@@ -220,3 +220,92 @@ def test_fp16_store_saturates(cuda_device):
     got = out[0].float()
     assert torch.isfinite(got).all()
     assert torch.all(got[:, 0::2] == 65504.0) and torch.all(got[:, 1::2] == -65504.0)
+
+
+# ---- 256-wide launches with many row tiles: these run on CTA pairs (tcgen05.mma.cta_group::2)
+# unless VP3D_PAIR=0; the expectations are the same either way.
+def test_wide_flat_gemm_many_tiles_odd_count(cuda_device):
+    """151 row tiles (odd: the last pair has one out-of-range member), ragged last tile, fp32 out."""
+    dev = cuda_device
+    M, K, n_pad = 128 * 150 + 37, 192, 512
+    a = _mk(M, K, 1, dev, 31)
+    g = torch.Generator().manual_seed(32)
+    w = ((torch.rand(n_pad, K, 1, generator=g) * 2 - 1) / K ** 0.5).to(dev)
+    wp = pack_weight(w, n_pad, K, 1)
+    _, out = conv_gemm(a, 1, M, K, wp, 1, K, n_pad, per_sample_tiles=False, tap_row_step=0,
+                       tap_col_step=0, out_rows=M, out_f32_cols=n_pad)
+    exp = planes_value(a).reshape(M, K) @ planes_value(wp)[0].T
+    assert not torch.isnan(out).any()
+    assert _scale_err(out, exp) < 2e-5
+
+
+@pytest.mark.parametrize("precision", [0, 3])
+def test_wide_strided_block_tail_with_tma_residual(cuda_device, precision):
+    """The eval cone schedule's block tail at 256-wide tiles: 3-tap conv over row regions, then a
+    1x1 conv + affine + ReLU + TMA-loaded residual, bf16 and fp16 storage; K = 1024 keeps the
+    operand pipeline wrapping many times per tile."""
+    dev = cuda_device
+    C, R = 256, 128 * 101 + 5            # R output rows, 3R input rows (tap-major regions)
+    dt = torch.float16 if precision == 3 else torch.bfloat16
+    g = torch.Generator().manual_seed(33)
+    x = ((torch.rand(3 * R, C, generator=g) * 2 - 1)).to(dev).to(dt).unsqueeze(0).contiguous()
+    w3 = ((torch.rand(C, C, 3, generator=g) * 2 - 1) / (3 * C) ** 0.5).to(dev)
+    w1 = ((torch.rand(C, C, 1, generator=g) * 2 - 1) / C ** 0.5).to(dev)
+
+    def pk(w):
+        co, ci, k = w.shape
+        return w.permute(2, 0, 1).contiguous().to(dt).unsqueeze(0).contiguous()
+    scale = (torch.rand(C, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(C, generator=g) * 0.1).to(dev)
+    h, _ = conv_gemm(x, 1, 3 * R, C, pk(w3), 3, C, C, per_sample_tiles=False, tap_row_step=R,
+                     tap_col_step=0, out_rows=R, scale=scale, shift=shift, relu=True,
+                     precision=precision)
+    xv = x[0].double()
+    acc = sum(xv[k * R:(k + 1) * R] @ pk(w3)[0, k].double().T for k in range(3))
+    h_exp = torch.relu(acc * scale.double() + shift.double())
+    ulp = 2 ** -11 if precision == 3 else 2 ** -8
+    assert torch.all((h[0].double() - h_exp).abs() <= h_exp.abs() * ulp + 1e-6)
+    y, _ = conv_gemm(h, 1, R, C, pk(w1), 1, C, C, per_sample_tiles=False, tap_row_step=0,
+                     tap_col_step=0, out_rows=R, scale=scale, shift=shift, relu=True, res=x,
+                     res_rows_per_sample=0, res_row_step=1, res_row_off=R, precision=precision)
+    acc = h[0].double() @ pk(w1)[0, 0].double().T
+    y_exp = torch.relu(acc * scale.double() + shift.double()) + xv[R:2 * R]
+    assert not torch.isnan(y[0].double()).any()
+    assert torch.all((y[0].double() - y_exp).abs() <= y_exp.abs() * ulp + 1e-6)
+
+
+def test_wide_dilated_tiles_and_stats(cuda_device):
+    """Per-sample tiles (dilated layout, 3 ragged tiles per sample, odd tile count) at 256-wide
+    tiles with the training epilogue: raw bf16 store + per-slab batch statistics."""
+    dev = cuda_device
+    C, samples, L, dil = 256, 51, 300 + 18, 9
+    Lout = L - 2 * dil
+    a = _mk(samples * L, C, 1, dev, 34)
+    g = torch.Generator().manual_seed(35)
+    w = ((torch.rand(C, C, 3, generator=g) * 2 - 1) / (3 * C) ** 0.5).to(dev)
+    wp = pack_weight(w, C, C, 1)
+    tiles = samples * ((Lout + 127) // 128)
+    stats = torch.full((4 * tiles, 2, C), float("nan"), dtype=torch.float32, device=dev)
+    out, _ = conv_gemm(a, samples, L, C, wp, 3, C, C, per_sample_tiles=True, tap_row_step=dil,
+                       tap_col_step=0, out_rows=Lout, stats=stats)
+    av = planes_value(a).reshape(samples * L, C)
+    acc = expected_conv(av, planes_value(wp), samples=samples, a_rows=L, taps=3, k_per_tap=C,
+                        per_sample_tiles=True, tap_row_step=dil, tap_col_step=0, out_rows=Lout)
+    assert torch.all((out[0].double() - acc).abs() <= acc.abs() * 2 ** -8 + 1e-6)
+    assert not torch.isnan(stats).any()
+    assert _scale_err(stats[:, 0].sum(0), acc.sum(0)) < 1e-4
+    assert _scale_err(stats[:, 1].sum(0), (acc * acc).sum(0)) < 1e-4
+
+
+def test_wide_bf16x3_two_planes(cuda_device):
+    dev = cuda_device
+    M, K, n_pad = 128 * 80 + 9, 256, 256
+    g = torch.Generator().manual_seed(36)
+    a32 = (torch.rand(M, K, generator=g) * 2 - 1).to(dev)
+    w32 = ((torch.rand(n_pad, K, 1, generator=g) * 2 - 1) / K ** 0.5).to(dev)
+    a = split_planes(a32, 2)
+    wp = pack_weight(w32, n_pad, K, 2)
+    out, _ = conv_gemm(a, 1, M, K, wp, 1, K, n_pad, per_sample_tiles=False, tap_row_step=0,
+                       tap_col_step=0, out_rows=M, precision=1, out_planes=2)
+    exp = a32.double() @ w32[:, :, 0].double().T
+    assert _scale_err(planes_value(out), exp) < 3e-5

@@ -156,8 +156,6 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   const uint64_t plane_stride = (uint64_t)d->samples * a_rows * a_ld;
   VP3D_TRY(make_map_4d(&ma, d->a, a_ld, a_rows, a_ld, d->samples, a_rows * a_ld, a_planes,
                        plane_stride, kBlockM));
-  VP3D_TRY(make_map_2d(&mw, d->w, d->k_per_tap, (uint64_t)w_planes * d->taps * d->n_pad, block_n));
-
   ConvGemmArgs g;
   memset(&g, 0, sizeof(g));
   g.dilated = d->per_sample_tiles ? 1 : 0;
@@ -273,6 +271,10 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     g.bnb_seed_hi = (unsigned)(d->bnb_seed >> 32);
     g.bnb_layer = (unsigned)d->bnb_layer;
   }
+  // W boxes: the whole N block, or half of it per CTA when the launch runs on CTA pairs
+  const bool pair = conv_gemm_uses_pair(g, block_n, num_sms());
+  VP3D_TRY(make_map_2d(&mw, d->w, d->k_per_tap, (uint64_t)w_planes * d->taps * d->n_pad,
+                       pair ? block_n / 2 : block_n));
   CUDA_TRY(launch_conv_gemm(ma, mw, mo, mr, mz, g, block_n, num_sms(), stream));
   return VP3D_OK;
 }

@@ -13,6 +13,16 @@
 //                   into the group's SWIZZLE_128B staging tile(s) -> TMA store (coalesced 128-byte
 //                   rows, clipped at the tensor edge by the tensor map)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// PAIR variant (BLOCK_N = 256): the grid is launched in clusters of two CTAs that compute a
+// 256-row x 256-column tile together with one tcgen05.mma.cta_group::2 stream issued by the
+// cluster's rank-0 CTA ("leader").  Each CTA TMA-loads its own 128-row A tile and HALF of the W tile
+// (128 of the 256 output channels) -- 16 + 16 KiB per k-block instead of 16 + 32 -- both crediting
+// the leader's `full` barrier; the leader's tcgen05.commit multicasts to both CTAs' `empty` /
+// accumulator-full barriers; the accumulator rows of each CTA live in its own TMEM and go through
+// its own epilogue, which releases the accumulator stage on the leader's barrier.  Per SM this cuts
+// the operand bytes per MMA by a third and deepens the operand pipeline (6 / 4 stages instead of
+// 4 / 3), which is what the operand-supply-bound 1x1 layers need.
 #include "conv_gemm.cuh"
 
 #include <stdlib.h>
@@ -27,11 +37,12 @@ namespace vp3d {
 // multiple of the number of N blocks so that a CTA keeps its N block for all of its tiles.
 // OUT2: two output planes (hi, lo) -> each epilogue group needs two staging tiles; the extra 32 KiB
 // come out of the operand pipeline.
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool PAIR = false>
 struct GemmCfg {
   static_assert(!(RES && WRES), "W-resident variant has no residual path");
+  static_assert(!PAIR || (BLOCK_N == 256 && !WRES), "CTA pairs run 256-wide, streamed-W tiles");
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
-  static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr uint32_t kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = WRES ? kABytes : kABytes + kBBytes;
   static constexpr uint32_t kWResBytes = WRES ? 128u * 1024u : 0u;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
@@ -44,12 +55,18 @@ struct GemmCfg {
   // depth)
   static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
   static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
-  // as many operand stages as fit below 224 KiB, at most 8
-  static constexpr int kStagesFit = (224u * 1024u - kFixedBytes) / kStageBytes;
+  // per-channel affine (scale, shift) of the current N block: 2 x BLOCK_N floats
+  static constexpr uint32_t kAffineBytes = 2 * BLOCK_N * 4;
+  static constexpr uint32_t kBarBytesMax = (2 * 8 + 4 + 8 + 1) * 8 + 32;
+  // as many operand stages as fit into the 227 KiB a CTA may use, at most 8
+  static constexpr uint32_t kMaxSmem = 232448u;
+  static constexpr int kStagesFit =
+      (kMaxSmem - kFixedBytes - kBarBytesMax - kAffineBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static_assert(kStages >= 2, "not enough shared memory for the operand pipeline");
-  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 8 + 1) * 8 + 16;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedBytes + kBarBytes + 1024;
+  static constexpr uint32_t kBarBytes = (2 * kStages + 4 + 8 + 1) * 8 + 32;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedBytes + kBarBytes + kAffineBytes;
+  static_assert(kSmemBytes <= kMaxSmem, "shared memory budget exceeded");
 };
 
 __device__ __forceinline__ void tile_coords(const ConvGemmArgs& p, int tile, int& n_blk,
@@ -108,21 +125,21 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
 
 // TRAIN compiles in the training-only epilogue paths (BatchNorm batch statistics of the stored
 // value, fused BatchNorm-backward reductions); eval launches use the leaner TRAIN = false build.
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_z, const ConvGemmArgs p) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBlocksPerTile = BLOCK_N / 64;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-  uint8_t* smem = smem_raw + (base - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);   // SWIZZLE_128B tiles need 1024 B alignment
+  if (base & 1023u) __trap();                 // (no slack is reserved for re-aligning)
+  uint8_t* smem = smem_raw;
 
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + kStages * Cfg::kABytes;  // WRES: the resident W slab
@@ -139,12 +156,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_slot = wfull_bar + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+  const uint32_t affine_off = (tmem_slot + 8 - base + 15u) & ~15u;   // [scale | shift][BLOCK_N]
+  float* s_affine = reinterpret_cast<float*>(smem + affine_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = p.dilated ? p.samples * p.tiles_per_sample : p.tiles_per_sample;
-  const int total_tiles = m_tiles * p.n_tiles;
+  // Work distribution.  A "worker" is a CTA, or a CTA pair; work item w covers N block w % n_tiles of
+  // row tile w / n_tiles (pairs: row tiles 2*(w / n_tiles) + rank; the odd row tile of an odd count
+  // is out of range for rank 1: its loads are zero-filled and its stores clipped by the tensor maps).
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
+  auto tile_of = [&](int w) -> int {   // work item -> this CTA's (row tile, N block) as m_blk*n_tiles+n_blk
+    if (!PAIR) return w;
+    return (2 * (w / p.n_tiles) + (int)cta_rank) * p.n_tiles + w % p.n_tiles;
+  };
   const int k_iters = p.pairs * p.taps * p.kblocks_per_tap;
   // auxiliary tiles per 64-column store block: the residual plane(s) and, for the fused
   // BatchNorm-backward reductions, the Z tile.  kResSlots / tiles stages are in flight.
@@ -168,7 +198,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s * 8, 1);
-      mbar_init(tempty_bar + s * 8, 256);  // both epilogue groups release an accumulator stage
+      // both epilogue groups release an accumulator stage (pairs: of both CTAs, on the leader's)
+      mbar_init(tempty_bar + s * 8, PAIR ? 512 : 256);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(rfull_bar + s * 8, 1);
@@ -178,10 +209,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Everything above touched only this CTA's shared memory / TMEM.  From here on global memory
@@ -206,24 +240,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       slab * p.n_pad + n_blk * BLOCK_N);
         }
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker; w < total_tiles; w += num_workers) {
         int n_blk, sample, row0;
-        tile_coords(p, tile, n_blk, sample, row0);
+        tile_coords(p, tile_of(w), n_blk, sample, row0);
         for (int pair = 0; pair < p.pairs; ++pair) {
           const int a_plane = (pair == 1) ? 1 : 0;
           const int w_plane = (pair == 2) ? 1 : 0;
           for (int tap = 0; tap < p.taps; ++tap) {
             const int a_row = row0 + tap * p.tap_row_step;
             const int a_col0 = tap * p.tap_col_step;
-            const int w_row = (w_plane * p.taps + tap) * p.n_pad + n_blk * BLOCK_N;
+            // pairs: this CTA streams the W rows of its half of the N block
+            const int w_row = (w_plane * p.taps + tap) * p.n_pad + n_blk * BLOCK_N +
+                              (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
             for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
               mbar_wait(empty_bar + stage * 8, phase ^ 1);
-              mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
-              tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
-                          a_col0 + kb * kBlockK, a_row, sample, a_plane);
-              if (!WRES)
-                tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
-                            kb * kBlockK, w_row);
+              if (PAIR) {
+                // both CTAs' tiles are credited to the leader's barrier (the MMA issuer waits there)
+                const uint32_t lbar = leader_cta_addr(full_bar + stage * 8);
+                if (is_leader) mbar_expect_tx(full_bar + stage * 8, 2 * Cfg::kStageBytes);
+                tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes,
+                                 a_col0 + kb * kBlockK, a_row, sample, a_plane);
+                tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
+              } else {
+                mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
+                tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
+                            a_col0 + kb * kBlockK, a_row, sample, a_plane);
+                if (!WRES)
+                  tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
+                              kb * kBlockK, w_row);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -232,14 +277,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && is_leader) {
+      constexpr int kMmaM = PAIR ? 2 * kBlockM : kBlockM;   // pairs: one 256-row MMA over both CTAs
       const uint32_t idesc =
-          p.f16 ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_bf16(kBlockM, BLOCK_N);
+          p.f16 ? make_idesc_f16(kMmaM, BLOCK_N) : make_idesc_bf16(kMmaM, BLOCK_N);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       if (WRES) mbar_wait(wfull_bar, 0);
       const int per_pair = p.taps * p.kblocks_per_tap;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker; w < total_tiles; w += num_workers) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -254,12 +300,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            umma_bf16_ss(d_tmem, desc_a + 2 * k, desc_b + 2 * k, idesc, (it | k) ? 1u : 0u);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, desc_a + 2 * k, desc_b + 2 * k, idesc, (it | k) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, desc_a + 2 * k, desc_b + 2 * k, idesc, (it | k) ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage * 8);  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if (PAIR) umma_commit_pair(empty_bar + stage * 8);
+          else umma_commit(empty_bar + stage * 8);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + acc * 8);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs of a pair)
+        if (PAIR) umma_commit_pair(tfull_bar + acc * 8);
+        else umma_commit(tfull_bar + acc * 8);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -267,9 +318,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ------------------------------------------------------------ auxiliary-tile producer
     if (RES && lane == 0) {
       uint32_t rs = 0, rphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker; w < total_tiles; w += num_workers) {
         int n_blk, sample, row0;
-        tile_coords(p, tile, n_blk, sample, row0);
+        tile_coords(p, tile_of(w), n_blk, sample, row0);
         for (int sb = 0; sb < kBlocksPerTile; ++sb) {
           const int col = n_blk * BLOCK_N + sb * 64;
           const bool res_here = has_res && col >= p.res_col_begin && col < p.res_col_begin + p.res_cols;
@@ -311,8 +362,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t sw = r_in_tile & 7;
     // this group's staging tile(s): [hi] or [hi, lo]
     const uint32_t my_store = smem_store + eg * (OUT2 ? 2 : 1) * Cfg::kTileBytes;
+    // accumulator release: on this CTA's barrier, or (pairs) on the leader's through the cluster window
+    const uint32_t tempty_addr = PAIR ? leader_cta_addr(tempty_bar) : tempty_bar;
+    int aff_n_blk = -1;               // N block whose scale / shift sit in shared memory
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int w = worker; w < total_tiles; w += num_workers) {
+      const int tile = tile_of(w);
       int n_blk, sample, row0;
       tile_coords(p, tile, n_blk, sample, row0);
       const int m_blk = tile / p.n_tiles;  // row-tile index: 4 slabs of 32 rows each
@@ -336,11 +391,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool two_planes_t =
           two_planes && (p.dilated || (row0 < p.lo_row_end && row0 + kBlockM > p.lo_row_begin));
 
+      // Per-channel affine of this N block: staged once in shared memory (all 32 lanes of a warp
+      // need the same 32 values per chunk: broadcast LDS instead of 16 global loads per chunk whose
+      // latency sat on the critical path).  Two 256-thread barriers per change of N block (nobody
+      // still reads the old values / the new ones are visible), none while it stays the same -- the
+      // usual case: the number of workers is a multiple of n_tiles.
+      if (do_affine && n_blk != aff_n_blk) {
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const int e = (int)threadIdx.x - 128;
+        if (e < BLOCK_N) {
+          s_affine[e] = __ldg(p.scale + n_blk * BLOCK_N + e);
+          s_affine[BLOCK_N + e] = __ldg(p.shift + n_blk * BLOCK_N + e);
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        aff_n_blk = n_blk;
+      }
+      const float* s_scale = s_affine;
+      const float* s_shift = s_affine + BLOCK_N;
+
+      // The last store block of this tile that this group owns: once its accumulator columns are in
+      // registers the TMEM stage is released, so the MMAs of the next-but-one tile overlap the math
+      // and the store of that block.  (A group that owns no block of the tile releases at once.)
+      int last_owned = -1;
+#pragma unroll
+      for (int sb = 0; sb < kBlocksPerTile; ++sb)
+        if (((gblock + (uint32_t)sb) & 1u) == (uint32_t)eg) last_owned = sb;
+
       // Both groups wait for the accumulator even when a tile holds no block for one of them: the
-      // release below must not run ahead of the MMAs that refill this TMEM stage.
+      // release must not run ahead of the MMAs that refill this TMEM stage.
       mbar_wait(tfull_bar + acc * 8, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+      if (last_owned < 0) {
+        tc_fence_before();
+        if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+      }
 
 #pragma unroll 1
       for (int sb = 0; sb < kBlocksPerTile; ++sb, ++gblock) {
@@ -359,16 +444,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int c0 = cb + half * 32;
           uint32_t raw[32];
           tmem_ld_32x32(t_addr + chunk * 32, raw);
+          // while the TMEM load is in flight: make sure the auxiliary tiles of this block have
+          // landed and fetch this row's residual bytes (plane 0) from shared memory
+          uint4 rres[4];
+          if (RES) {
+            if (aux_here && half == 0) {
+              // The previous use of this stage may belong to the other epilogue group.  A parity
+              // wait only tells "one phase ahead" from "done", so first make sure that use has been
+              // released (which implies its fill completed); then the fill wait is unambiguous.
+              if (ruse > 0) mbar_wait(rempty_bar + rs * 8, (ruse - 1) & 1u);
+              mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
+            }
+            if (res_here) {
+              const uint32_t src = smem_res + (rs * aux_tiles) * Cfg::kTileBytes + stage_row;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rres[q] = ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4));
+            }
+          }
           tmem_ld_wait();
+          if (sb == last_owned && half == 1) {
+            // every accumulator column this thread needs from the tile is in registers
+            tc_fence_before();
+            if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+          }
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
           if (do_affine) {
+            const int cl = c0 - n_blk * BLOCK_N;   // column inside the N block
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + j));
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + cl + j);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + cl + j);
               v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
               v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
               v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
@@ -380,21 +488,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
           if (RES) {
-            if (aux_here && half == 0) {
-              // The previous use of this stage may belong to the other epilogue group.  A parity
-              // wait only tells "one phase ahead" from "done", so first make sure that use has been
-              // released (which implies its fill completed); then the fill wait is unambiguous.
-              if (ruse > 0) mbar_wait(rempty_bar + rs * 8, (ruse - 1) & 1u);
-              mbar_wait(rfull_bar + rs * 8, rphase);  // tiles have landed
-            }
             if (res_here) {
-              for (int pl = 0; pl < p.res_planes; ++pl) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (f16) add_f16x8(v + q * 8, rres[q]); else add_bf16x8(v + q * 8, rres[q]);
+              }
+              for (int pl = 1; pl < p.res_planes; ++pl) {   // lo plane of a split-bf16 residual
                 const uint32_t src = smem_res + (rs * aux_tiles + pl) * Cfg::kTileBytes + stage_row;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint4 u = ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4));
-                  if (f16) add_f16x8(v + q * 8, u); else add_bf16x8(v + q * 8, u);
-                }
+                for (int q = 0; q < 4; ++q)
+                  add_bf16x8(v + q * 8, ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4)));
               }
             }
           } else if (res_here && res_ok) {
@@ -519,9 +622,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             // per-slab partials (slab = 32 rows of this tile), summed in a fixed order by
             // launch_ordered_col_sums: run-to-run reproducible, unlike atomics
-            float* bp = p.bnb_sums + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
-            bp[0] = s[0];
-            bp[p.n_pad] = q2[0];  // x invstd is applied after the ordered sum
+            if (m_blk < m_tiles) {   // (a pair's odd row tile has no slab)
+              float* bp = p.bnb_sums + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
+              bp[0] = s[0];
+              bp[p.n_pad] = q2[0];  // x invstd is applied after the ordered sum
+            }
           }
           if (RES && aux_here && half == 1)
             mbar_arrive(rempty_bar + rs * 8);  // this thread is done with the auxiliary stage
@@ -551,14 +656,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // per-slab (32 rows) sum and sum of squares; bn_stats_finalize turns each slab into
             // (count, mean, M2) and merges the slabs in a fixed order (Chan et al.): reproducible,
             // and free of the E[x^2] - E[x]^2 cancellation over the whole batch
-            float* sp = p.stats + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
-            sp[0] = s[0];
-            sp[p.n_pad] = q[0];
+            if (m_blk < m_tiles) {   // (a pair's odd row tile has no slab)
+              float* sp = p.stats + ((size_t)(m_blk * 4 + ew) * 2) * p.n_pad + c0 + lane;
+              sp[0] = s[0];
+              sp[p.n_pad] = q[0];
+            }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar + acc * 8);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     // the staging tiles must outlive every bulk store that reads them
@@ -567,10 +672,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  // pairs: neither CTA may leave (or free TMEM) while the other can still read its shared memory
+  // through the pair MMAs or signal its barriers
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -587,13 +695,23 @@ static bool pdl_enabled() {
   return v != 0;
 }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN>
+// CTA pairs (cta_group::2) for the 256-wide streamed-W launches: VP3D_PAIR=0 turns them off.
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VP3D_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN, PAIR>;
   // the dynamic shared memory opt-in is a per-device attribute
   static bool attr_set[kMaxDevices] = {};
   int dev = 0;
@@ -606,40 +724,68 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
     attr_set[dev] = true;
   }
   const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
-  const int total = m_tiles * args.n_tiles;
+  const int total = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * args.n_tiles;
   if (total <= 0) return cudaSuccess;
-  int grid = total < num_sms ? total : num_sms;
-  if (WRES) grid = grid / args.n_tiles * args.n_tiles;  // a CTA keeps its N block for every tile
+  const int max_workers = PAIR ? num_sms / 2 : num_sms;
+  int workers = total < max_workers ? total : max_workers;
+  if (WRES) workers = workers / args.n_tiles * args.n_tiles;  // a CTA keeps its N block for every tile
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.gridDim = dim3(PAIR ? 2 * workers : workers, 1, 1);
   cfg.blockDim = dim3(384, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  if (PAIR) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n_attr;
   return cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
 }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool PAIR>
 static cudaError_t launch_train(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
                                 const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
                                 int num_sms, cudaStream_t stream) {
   if ((args.flags & kEpiStats) || args.bnb)
-    return launch_impl<BLOCK_N, RES, WRES, OUT2, true>(a, w, o, r, z, args, num_sms, stream);
-  return launch_impl<BLOCK_N, RES, WRES, OUT2, false>(a, w, o, r, z, args, num_sms, stream);
+    return launch_impl<BLOCK_N, RES, WRES, OUT2, true, PAIR>(a, w, o, r, z, args, num_sms, stream);
+  return launch_impl<BLOCK_N, RES, WRES, OUT2, false, PAIR>(a, w, o, r, z, args, num_sms, stream);
 }
 
-template <int BLOCK_N, bool RES, bool WRES>
+template <int BLOCK_N, bool RES, bool WRES, bool PAIR = false>
 static cudaError_t launch_planes(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
                                  const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
                                  int num_sms, cudaStream_t stream) {
   if (args.out_planes == 2 && !(args.flags & kEpiOutF32))
-    return launch_train<BLOCK_N, RES, WRES, true>(a, w, o, r, z, args, num_sms, stream);
-  return launch_train<BLOCK_N, RES, WRES, false>(a, w, o, r, z, args, num_sms, stream);
+    return launch_train<BLOCK_N, RES, WRES, true, PAIR>(a, w, o, r, z, args, num_sms, stream);
+  return launch_train<BLOCK_N, RES, WRES, false, PAIR>(a, w, o, r, z, args, num_sms, stream);
+}
+
+// Whether launch_conv_gemm will run this launch on CTA pairs (the W tensor map must then be built
+// with 128-row boxes: each CTA of a pair loads half of the N block).
+bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms) {
+  if (!pair_enabled() || block_n != 256 || (num_sms & 1)) return false;
+  const bool res = args.res_tma != 0 || args.bnb != 0;
+  const int m_tiles = args.dilated ? args.samples * args.tiles_per_sample : args.tiles_per_sample;
+  const long long w_bytes = (long long)(args.pairs == 3 ? 2 : 1) * args.taps * args.kblocks_per_tap *
+                            block_n * kBlockK * 2;
+  const bool wres = !res && w_bytes <= 128 * 1024 &&
+                    (long long)m_tiles * args.n_tiles >= 4LL * num_sms && args.n_tiles <= num_sms;
+  if (wres) return false;
+  if (res && args.out_planes == 2) return false;
+  // a pair needs two row tiles to share an N block; tiny launches keep single CTAs
+  return m_tiles >= 2;
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
@@ -655,11 +801,16 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
                     (long long)m_tiles * args.n_tiles >= 4LL * num_sms && args.n_tiles <= num_sms;
   switch (block_n) {
     case 256:
+      if (conv_gemm_uses_pair(args, block_n, num_sms)) {
+        if (res)
+          return launch_train<256, true, false, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+        return launch_planes<256, false, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+      }
       if (wres) return launch_planes<256, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
       if (res) {
         // (two output planes next to a TMA residual always run on 128-wide tiles, see run_conv)
         if (args.out_planes == 2) return cudaErrorInvalidConfiguration;
-        return launch_train<256, true, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
+        return launch_train<256, true, false, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
       }
       return launch_planes<256, false, false>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
     case 128:

@@ -105,6 +105,9 @@ struct ConvGemmArgs {
 // tmap_res: 4-D (channel, row, sample, plane) over the residual's row view, box (64, 128, 1, 1); used
 // only when args.res_tma is set.
 // tmap_z: same geometry as tmap_out over the Z tensor of the layer below; used only when args.bnb.
+// tmap_w: box rows = block_n, or block_n / 2 when conv_gemm_uses_pair() says the launch runs on CTA
+// pairs (each CTA of a pair loads its half of the N block).
+bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms);
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,

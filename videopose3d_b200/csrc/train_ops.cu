@@ -460,7 +460,7 @@ pack_conv_weight_t_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict
   }
 }
 
-RowTiling row_tiling(long long rows, int c, dim3& grid) {
+RowTiling row_tiling(long long rows, int c, dim3& grid, int min_rows = 0) {
   RowTiling tl;
   const int groups = c / 8;
   tl.G = 8;
@@ -472,6 +472,7 @@ RowTiling row_tiling(long long rows, int c, dim3& grid) {
   long long rpb = rows * col_blocks / (16 * 148);
   if (rpb > 256) rpb = 256;
   if (rpb < 4LL * lanes) rpb = 4LL * lanes;
+  if (rpb < min_rows) rpb = min_rows;
   rpb = (rpb + lanes - 1) / lanes * lanes;
   tl.rows_per_block = (int)rpb;
   grid = dim3(col_blocks, (unsigned)((rows + rpb - 1) / rpb));
@@ -533,7 +534,8 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, cons
                                  unsigned* counter, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   dim3 grid;
-  const RowTiling tl = row_tiling(rows, c, grid);
+  // >= 32 rows per block: the per-block partials then fit the slab-partial buffer (rows / 32 slabs)
+  const RowTiling tl = row_tiling(rows, c, grid, 32);
   if ((size_t)grid.y * 2 * c > partial_floats) return cudaErrorInvalidValue;
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
                                                  shift, mean, invstd, drop, partials, tl);
