@@ -58,6 +58,20 @@ CASES = {
                                N=40, T=27, train=True, momentum=0.05),
     "opt_35_c128_train_causal": dict(cls="TemporalModelOptimized1f", J=16, F=2, Jout=16, fw=[3, 5],
                                      C=128, N=70, T=15, train=True, momentum=0.1, causal=True),
+    # channel counts that are not multiples of 64 (run.py -ch accepts any value, arguments.py:47)
+    "tm_333_c100": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=100, N=3, T=40),
+    "opt_333_c100": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=100, N=6,
+                         T=27),
+    "opt_33_c40_train": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3], C=40,
+                             N=50, T=9, train=True, momentum=0.1),
+    "tm_33_c100_train": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3], C=100, N=4, T=20,
+                             train=True, momentum=0.1),
+    # strided model on inputs longer than one receptive field: Conv1d(stride=w) floors away the
+    # trailing frames (model.py:167, 178)
+    "opt_333_c64_t30": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 3, 3], C=64, N=4,
+                            T=30),
+    "opt_35_c64_t17_causal": dict(cls="TemporalModelOptimized1f", J=17, F=2, Jout=17, fw=[3, 5], C=64,
+                                  N=3, T=17, causal=True),
     # BASELINE configs[0]: arc 3,3,3, 17 joints, N=64, CPU fp32 forward (C = 1024)
     "cfg1_tm_333_c1024": dict(cls="TemporalModel", J=17, F=2, Jout=17, fw=[3, 3, 3], C=1024, N=64,
                               T=27, store_sd=False),

@@ -229,3 +229,31 @@ def test_errors(cuda_device):
         m(torch.zeros(2, 30, 17, 2))                        # CPU tensor: no fallback
     with pytest.raises(AssertionError):
         vp.TemporalModel(17, 2, 17, [3, 4, 3])
+
+
+def test_strided_model_reproduces_reference_size_mismatch_error(cuda_device):
+    """Optimized1f on a length whose residual slice and strided conv disagree (T = 33, arc 3,3,3:
+    11 frames after expand -> conv gives 3, x[:, :, 1::3] gives 4): the reference raises a size
+    mismatch in `res + x` (model.py:191-194); so does the C ABI, with the same message."""
+    meta, sd, x, _, _ = load_golden("opt_333_c64")
+    m = _build(meta, sd, cuda_device, "fp16")
+    with pytest.raises((ValueError, RuntimeError), match="must match the size of tensor b"):
+        m(torch.zeros(2, 33, 17, 2, device=cuda_device))
+    y = m(torch.zeros(2, 30, 17, 2, device=cuda_device))   # 30 = 27 + ignored trailing frames: fine
+    assert tuple(y.shape) == (2, 1, 17, 3)
+
+
+def test_any_channel_count(cuda_device):
+    """`channels` need not be a multiple of 64 (run.py -ch N): odd sizes against the oracle."""
+    for C in (1, 17, 96, 129):
+        sd = orc.make_state_dict(17, 2, 17, [3, 3], C, seed=40 + C)
+        x = orc.make_input(5, 13, 17, 2, seed=3)
+        y_ref = orc.forward_numpy(sd, x.numpy(), [3, 3])
+        m = vp.TemporalModel(17, 2, 17, filter_widths=[3, 3], channels=C)
+        m.load_state_dict(sd)
+        m = m.to(cuda_device).eval()
+        with torch.no_grad():
+            y16 = m(x.to(cuda_device)).cpu().numpy()
+            y3 = m.set_precision("bf16x3")(x.to(cuda_device)).cpu().numpy()
+        assert _rel(y3, y_ref) <= 1e-4, C
+        assert _rel(y16, y_ref) <= 1e-3, C

@@ -314,9 +314,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
       return fail(VP3D_ERR_INVALID, "Only odd filter widths are supported");  // model.py:20-21
   if (cfg->num_joints_in < 1 || cfg->in_features < 1 || cfg->num_joints_out < 1)
     return fail(VP3D_ERR_INVALID, "plan_create: joint / feature counts must be positive");
-  if (cfg->channels < 64 || cfg->channels % 64)
-    return fail(VP3D_ERR_UNSUPPORTED, "channels must be a positive multiple of 64 (got %d)",
-                cfg->channels);
+  if (cfg->channels < 1)
+    return fail(VP3D_ERR_INVALID, "channels must be positive (got %d)", cfg->channels);
   if (cfg->precision < VP3D_PRECISION_BF16 || cfg->precision > VP3D_PRECISION_FP16)
     return fail(VP3D_ERR_INVALID, "plan_create: unknown precision %d", cfg->precision);
   if (cfg->variant != VP3D_VARIANT_DILATED && cfg->variant != VP3D_VARIANT_STRIDED)
@@ -330,7 +329,11 @@ extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3
   vp3d_plan* p = new vp3d_plan();
   p->cfg = *cfg;
   p->nb = cfg->num_widths - 1;
-  p->C = cfg->channels;
+  // any `channels` (the reference takes any -ch, arguments.py:47): activations and packed weights
+  // are laid out with the channel count padded to 64; padding channels carry zero weights and a
+  // zero affine, so they stay exactly zero through every layer
+  p->c_real = cfg->channels;
+  p->C = round_up(cfg->channels, 64);
   p->c_in_raw = cfg->num_joints_in * cfg->in_features;
   p->c_out_raw = cfg->num_joints_out * 3;
   p->c_in_pad = round_up(p->c_in_raw, 64);
@@ -431,9 +434,9 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
   if (what & VP3D_PACK_CONV) {
     if (!w->expand_conv_weight || !w->shrink_weight)
       return fail(VP3D_ERR_INVALID, "set_weights: missing conv weights");
-    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->C,
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->c_real,
                                      p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream, p->f16));
-    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->c_real,
                                      p->c_in_raw, w0, p->C, p->k0_pad, 1, stream, p->f16));
     // with VP3D_PACK_CONV_T the transposed-pack kernels below also write these forward packs
     const bool fused = (what & VP3D_PACK_CONV_T) != 0;
@@ -442,13 +445,15 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
         return fail(VP3D_ERR_INVALID, "set_weights: missing layers_conv.%d", 2 * i);
       if (fused) continue;
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i], p->conv[2 * i].w, p->planes,
-                                       p->C, p->C, p->taps[i + 1], p->C, p->C, 0, stream, p->f16));
+                                       p->c_real, p->c_real, p->taps[i + 1], p->C, p->C, 0, stream,
+                                       p->f16));
       CUDA_TRY(launch_pack_conv_weight(w->layers_conv_weight[2 * i + 1], p->conv[2 * i + 1].w,
-                                       p->planes, p->C, p->C, 1, p->C, p->C, 0, stream, p->f16));
+                                       p->planes, p->c_real, p->c_real, 1, p->C, p->C, 0, stream,
+                                       p->f16));
     }
     if (!fused)
-      CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw, p->C,
-                                       1, p->c_out_pad, p->C, 0, stream, p->f16));
+      CUDA_TRY(launch_pack_conv_weight(w->shrink_weight, p->shrink.w, p->planes, p->c_out_raw,
+                                       p->c_real, 1, p->c_out_pad, p->C, 0, stream, p->f16));
     p->conv_packed = true;
   }
   if (what & VP3D_PACK_BN_EVAL) {
@@ -457,13 +462,13 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_weights(vp3d_plan
       if (!w->expand_bn[k]) return fail(VP3D_ERR_INVALID, "set_weights: missing expand_bn");
     if (!w->shrink_bias) return fail(VP3D_ERR_INVALID, "set_weights: missing shrink.bias");
     CUDA_TRY(launch_bn_fold(w->expand_bn[0], w->expand_bn[1], w->expand_bn[2], w->expand_bn[3], eps,
-                            p->expand_dil.scale, p->expand_dil.shift, p->C, p->C, stream));
+                            p->expand_dil.scale, p->expand_dil.shift, p->c_real, p->C, stream));
     for (int l = 0; l < 2 * p->nb; ++l) {
       for (int k = 0; k < 4; ++k)
         if (!w->layers_bn[l][k]) return fail(VP3D_ERR_INVALID, "set_weights: missing layers_bn.%d", l);
       CUDA_TRY(launch_bn_fold(w->layers_bn[l][0], w->layers_bn[l][1], w->layers_bn[l][2],
-                              w->layers_bn[l][3], eps, p->conv[l].scale, p->conv[l].shift, p->C,
-                              p->C, stream));
+                              w->layers_bn[l][3], eps, p->conv[l].scale, p->conv[l].shift,
+                              p->c_real, p->C, stream));
     }
     CUDA_TRY(launch_bias_affine(w->shrink_bias, p->shrink.scale, p->shrink.shift, p->c_out_raw,
                                 p->c_out_pad, stream));
@@ -493,6 +498,8 @@ int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
   if (strided) {
     L[0] = T / fw[0];  // Conv1d(stride=w, kernel=w): floor((T - w)/w) + 1
     for (int i = 1; i <= p->nb; ++i) L[i] = L[i - 1] / fw[i];
+    // (when T is not exactly one receptive field the floors drop trailing frames layer by layer;
+    // strided_trim() below tells which rows the output actually depends on)
   } else {
     L[0] = T - (fw[0] - 1);
     for (int i = 1; i <= p->nb; ++i) L[i] = L[i - 1] - 2 * p->pad[i];
@@ -502,6 +509,29 @@ int layer_rows(const vp3d_plan* p, int T, bool strided, int* L) {
   return L[p->nb];
 }
 
+}  // namespace vp3d
+
+namespace vp3d {
+// Strided model on an input whose length is not a multiple of the widths, as Conv1d(stride = w)
+// handles it (model.py:167, 178, 191): every conv floors its output length, i.e. ignores trailing
+// frames, and the residual slice x[:, :, shift + w//2 :: w] must come out with the conv's length
+// (otherwise the reference's `res + x` raises a size mismatch -- reproduced here as an error).
+// On success L[] is trimmed to the rows the output depends on: L[i-1] = w_i * L[i], so that the
+// row-region (tap-major) schedule applies; in eval mode (running statistics) dropping the unused
+// rows changes nothing.  Returns VP3D_OK / an error status with the reference's message.
+int strided_trim(const vp3d_plan* p, int* L) {
+  const int* fw = p->cfg.filter_widths;
+  for (int i = 1; i <= p->nb; ++i) {
+    const int first = p->shift_str[i] + fw[i] / 2;
+    const int res_len = L[i - 1] > first ? (L[i - 1] - first + fw[i] - 1) / fw[i] : 0;
+    if (res_len != L[i])
+      return fail(VP3D_ERR_INVALID, "The size of tensor a (%d) must match the size of tensor b (%d) "
+                  "at non-singleton dimension 2 (residual slice of block %d on %d frames, width %d)",
+                  res_len, L[i], i, L[i - 1], fw[i]);
+  }
+  for (int i = p->nb; i >= 1; --i) L[i - 1] = fw[i] * L[i];
+  return VP3D_OK;
+}
 }  // namespace vp3d
 
 extern "C" __attribute__((visibility("default"))) int vp3d_output_frames(const vp3d_plan* p, int T) {
@@ -536,6 +566,7 @@ extern "C" __attribute__((visibility("default"))) size_t vp3d_workspace_bytes(co
   int L[VP3D_MAX_WIDTHS];
   const bool strided = use_strided(p, T);
   if (!layer_rows(p, T, strided, L)) return 0;
+  if (strided && strided_trim(p, L) != VP3D_OK) return 0;
   return ws_layout(p, N, T, strided, L).total;
 }
 
@@ -551,6 +582,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   if (!layer_rows(p, T, strided, L))
     return fail(VP3D_ERR_INVALID, "forward_eval: sequence of %d frames is shorter than the "
                 "receptive field (%d)", T, vp3d_receptive_field(p));
+  if (strided) VP3D_TRY(strided_trim(p, L));   // trailing frames the strided convs ignore
   const WsLayout wl = ws_layout(p, N, T, strided, L);
   if (!ws || ws_bytes < wl.total) return fail(VP3D_ERR_WORKSPACE, "workspace too small: %zu < %zu",
                                               ws_bytes, wl.total);
@@ -637,10 +669,6 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
     perm.levels = p->nb;
     perm.last_rows = L[p->nb];
     for (int i = 1; i <= p->nb; ++i) {
-      if (L[i - 1] != fw[i] * L[i])  // trailing frames that do not fill a stride group
-        return fail(VP3D_ERR_UNSUPPORTED,
-                    "strided schedule needs layer lengths divisible by the filter width "
-                    "(block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
       perm.region[i - 1] = (unsigned)R[i];
       perm.width[i - 1] = fw[i];
     }

@@ -69,7 +69,9 @@ int launch_adam_pack(const AdamPackItem* items, int n, int planes, int64_t step,
 struct vp3d_plan {
   vp3d_config cfg;
   int nb = 0;  // residual blocks
-  int C = 0, c_in_raw = 0, c_out_raw = 0, c_in_pad = 0, k0_pad = 0, c_out_pad = 0;
+  int C = 0;        // channels of the residual stream as laid out in memory: padded to 64
+  int c_real = 0;   // the model's `channels` argument (any positive value, model.py:85-86)
+  int c_in_raw = 0, c_out_raw = 0, c_in_pad = 0, k0_pad = 0, c_out_pad = 0;
   int planes = 1;
   int f16 = 0;  // VP3D_PRECISION_FP16: 16-bit stores hold IEEE fp16
   int pad[VP3D_MAX_WIDTHS];
@@ -112,6 +114,7 @@ int plan_alloc(vp3d_plan* p, void** out, size_t bytes);
 bool use_strided(const vp3d_plan* p, int T);
 // rows per sample after each stage: L[0] = rows out of expand, L[i] = rows out of block i
 int layer_rows(const vp3d_plan* p, int T, bool strided, int* L);
+int strided_trim(const vp3d_plan* p, int* L);
 void train_state_destroy(TrainState* t);
 int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stream,
                           bool also_forward);

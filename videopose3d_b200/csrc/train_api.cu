@@ -240,14 +240,14 @@ int train_pack_transposed(vp3d_plan* p, const vp3d_weights* w, cudaStream_t stre
   TrainState* t = p->train;
   for (int i = 0; i < p->nb; ++i) {
     CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i], t->conv_t[2 * i], p->planes,
-                                       p->C, p->C, p->taps[i + 1], p->C, p->C, stream,
+                                       p->c_real, p->c_real, p->taps[i + 1], p->C, p->C, stream,
                                        also_forward ? p->conv[2 * i].w : nullptr, p->C, p->C));
     CUDA_TRY(launch_pack_conv_weight_t(w->layers_conv_weight[2 * i + 1], t->conv_t[2 * i + 1],
-                                       p->planes, p->C, p->C, 1, p->C, p->C, stream,
+                                       p->planes, p->c_real, p->c_real, 1, p->C, p->C, stream,
                                        also_forward ? p->conv[2 * i + 1].w : nullptr, p->C, p->C));
   }
-  CUDA_TRY(launch_pack_conv_weight_t(w->shrink_weight, t->shrink_t, p->planes, p->c_out_raw, p->C, 1,
-                                     p->C, c_out_pad128(p), stream,
+  CUDA_TRY(launch_pack_conv_weight_t(w->shrink_weight, t->shrink_t, p->planes, p->c_out_raw,
+                                     p->c_real, 1, p->C, c_out_pad128(p), stream,
                                      also_forward ? p->shrink.w : nullptr, p->c_out_pad, p->C));
   t->packed_t = true;
   return VP3D_OK;
@@ -290,7 +290,10 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
   for (int i = 1; strided && i <= p->nb; ++i)
     if (L[i - 1] != fw[i] * L[i])
       return fail(VP3D_ERR_UNSUPPORTED, "strided training needs layer lengths divisible by the "
-                  "filter width (block %d: %d frames, width %d)", i, L[i - 1], fw[i]);
+                  "filter width (block %d: %d frames, width %d): the BatchNorm batch statistics of "
+                  "a layer include the trailing frames its consumer ignores, which the flat row "
+                  "layout cannot express; run.py always trains on exactly one receptive field",
+                  i, L[i - 1], fw[i]);
   const TrainLayout wl = train_layout(p, N, T, L);
   if (!ws || ws_bytes < wl.total)
     return fail(VP3D_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes, wl.total);
@@ -329,7 +332,7 @@ VP3D_API int vp3d_forward_train(vp3d_plan* p, const float* x, float* y, int N, i
                                       per_sample_rows ? per_sample_rows : (int)rows, tps, bnp[0],
                                       bnp[1], const_cast<float*>(bnp[2]), const_cast<float*>(bnp[3]),
                                       bn_momentum[layer], 1e-5f, v.scale, v.shift, v.mean, v.invstd,
-                                      C, t->red_scratch, t->red_counter, stream));
+                                      C, p->c_real, t->red_scratch, t->red_counter, stream));
     CUDA_TRY(launch_bn_apply(z, rows * C, out, rows * C, pl, rows, C, v.scale, v.shift,
                              drop_cfg(t, layer), res, res_plane, map, stream));
     launches += 2;
@@ -429,7 +432,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   TrainState* t = p->train;
   if (!t || !t->have_forward) return fail(VP3D_ERR_STATE, "backward: no training forward to match");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int N = t->N, C = p->C, pl = p->planes;
+  const int N = t->N, C = p->C, Cr = p->c_real, pl = p->planes;   // padded / real channels
   const int* L = t->L;
   const int* fw = p->cfg.filter_widths;
   const bool strided = p->cfg.variant == VP3D_VARIANT_STRIDED;
@@ -497,7 +500,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     }
     CUDA_TRY(launch_bn_bwd_apply(gin, rows * C, z, rows * C, bf(wl.dz), rows * C, pl, rows, C,
                                  v.scale, v.shift, v.mean, v.invstd, dc, v.sums, dgamma, dbeta,
-                                 stream));
+                                 p->c_real, stream));
     ++launches;
     return VP3D_OK;
   };
@@ -511,7 +514,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   {
     WgradCall c;
     c.dz = bf(wl.dyp); c.dz_ld = co128; c.x = bf(wl.x[p->nb]); c.x_ld = C; c.rows = rows_top;
-    c.c_out = p->c_out_raw; c.c_in_cols = C; c.c_in = C; c.grad = g->shrink_weight;
+    c.c_out = p->c_out_raw; c.c_in_cols = Cr; c.c_in = Cr; c.grad = g->shrink_weight;
     VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
   }
   launches += 2;
@@ -537,7 +540,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     {
       WgradCall c;
       c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.h[i]); c.x_ld = C; c.rows = rows;
-      c.c_out = C; c.c_in_cols = C; c.c_in = C; c.grad = g->layers_conv_weight[c2];
+      c.c_out = Cr; c.c_in_cols = Cr; c.c_in = Cr; c.grad = g->layers_conv_weight[c2];
       VP3D_TRY(run_wgrad(p, c, partial, wl.partial_bytes, stream));
     }
     launches += 2;
@@ -554,7 +557,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
     {
       WgradCall c;
       c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.x[i - 1]); c.taps = p->taps[i];
-      c.c_out = C; c.c_in_cols = C; c.c_in = C; c.taps_out = p->taps[i];
+      c.c_out = Cr; c.c_in_cols = Cr; c.c_in = Cr; c.taps_out = p->taps[i];
       c.grad = g->layers_conv_weight[c1];
       if (strided) {
         c.x_ld = fw[i] * C; c.rows = rows; c.tap_col_step = C;
@@ -599,7 +602,7 @@ static int backward_impl(vp3d_plan* p, const float* dy, const vp3d_grads* g, voi
   VP3D_TRY(bn_bwd(0, wl.rows[0], gb[cur], bf(wl.z[0]), g->expand_bn[0], g->expand_bn[1]));
   {
     WgradCall c;
-    c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.a0); c.c_out = C; c.c_in = p->c_in_raw;
+    c.dz = bf(wl.dz); c.dz_ld = C; c.x = bf(wl.a0); c.c_out = Cr; c.c_in = p->c_in_raw;
     c.taps_out = fw[0]; c.grad = g->expand_conv_weight;
     if (strided) {
       c.x_ld = p->k0_pad; c.rows = wl.rows[0]; c.c_in_cols = fw[0] * p->c_in_raw; c.merged = 1;
@@ -645,13 +648,13 @@ VP3D_API int vp3d_adam_step_packed(vp3d_plan* p, const vp3d_weights* w,
       if (a.param != w->layers_conv_weight[l] || !a.param) continue;
       const int taps = (l % 2 == 0) ? p->taps[l / 2 + 1] : 1;
       it.fwd = p->conv[l].w; it.tr = t->conv_t[l];
-      it.c_out = p->C; it.c_in = p->C; it.taps = taps;
+      it.c_out = p->c_real; it.c_in = p->c_real; it.taps = taps;
       it.fwd_n_pad = p->C; it.fwd_k_pad = p->C; it.tr_n_pad = p->C; it.tr_k_pad = p->C;
       is_conv = true;
     }
     if (!is_conv && a.param && a.param == w->shrink_weight) {
       it.fwd = p->shrink.w; it.tr = t->shrink_t;
-      it.c_out = p->c_out_raw; it.c_in = p->C; it.taps = 1;
+      it.c_out = p->c_out_raw; it.c_in = p->c_real; it.taps = 1;
       it.fwd_n_pad = p->c_out_pad; it.fwd_k_pad = p->C;
       it.tr_n_pad = p->C; it.tr_k_pad = c_out_pad128(p);
       is_conv = true;
@@ -666,9 +669,9 @@ VP3D_API int vp3d_adam_step_packed(vp3d_plan* p, const vp3d_weights* w,
                             weight_decay, stream));
   if (expand_seen) {  // 104 k elements: the two expand packs (dilated / tap-merged) the usual way
     const int w0 = p->cfg.filter_widths[0];
-    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->C,
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_dil.w, p->planes, p->c_real,
                                      p->c_in_raw, w0, p->C, p->c_in_pad, 0, stream));
-    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->C,
+    CUDA_TRY(launch_pack_conv_weight(w->expand_conv_weight, p->expand_flat.w, p->planes, p->c_real,
                                      p->c_in_raw, w0, p->C, p->k0_pad, 1, stream));
   }
   p->last_launches = (plain.empty() ? 0 : 1) + (packed.empty() ? 0 : 1) + (expand_seen ? 2 : 0);

@@ -110,7 +110,7 @@ __device__ __forceinline__ bool last_block_of_group(unsigned* counter, int split
 
 __global__ void __launch_bounds__(256)
 bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geom, int c,
-                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         int c_real, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          float momentum, float eps, float* __restrict__ scale,
                          float* __restrict__ shift, float* __restrict__ mean_out,
@@ -158,6 +158,10 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geo
     return;
   }
   if (ch >= c) return;
+  if (ch >= c_real) {   // padding channel (channels not a multiple of 64): identically zero
+    scale[ch] = 0.0f; shift[ch] = 0.0f; mean_out[ch] = 0.0f; invstd[ch] = 0.0f;
+    return;
+  }
   const double n = (double)acc.n;
   const double m = (double)acc.mean;
   double var = n > 0.0 ? (double)acc.m2 / n : 0.0;
@@ -364,7 +368,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
                     int c, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     DropoutCfg drop, const float* __restrict__ sums, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, RowTiling tl) {
+                    float* __restrict__ dbeta, int c_real, RowTiling tl) {
   const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
   const int c0 = (blockIdx.x * tl.G + cg) * 8;
   const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
@@ -385,6 +389,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
     if (blockIdx.y == 0 && rl == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (c0 + j >= c_real) break;   // gradient tensors hold the model's real channel count
         if (dbeta) dbeta[c0 + j] = s1[j];
         if (dgamma) dgamma[c0 + j] = s2[j];
       }
@@ -492,12 +497,12 @@ cudaError_t launch_bn_stats_finalize(const float* part, int slabs, int dilated, 
                                      int tiles_per_sample, const float* gamma, const float* beta,
                                      float* running_mean, float* running_var, float momentum,
                                      float eps, float* scale, float* shift, float* mean,
-                                     float* invstd, int c, float* scratch, unsigned* counter,
-                                     cudaStream_t stream) {
+                                     float* invstd, int c, int c_real, float* scratch,
+                                     unsigned* counter, cudaStream_t stream) {
   if (c > kReduceMaxChannels) return cudaErrorInvalidValue;
   SlabGeom g = {dilated, out_rows, tiles_per_sample};
   const dim3 grid((c + 31) / 32, pick_splits(slabs));
-  bn_stats_finalize_kernel<<<grid, 256, 0, stream>>>(part, slabs, g, c, gamma, beta, running_mean,
+  bn_stats_finalize_kernel<<<grid, 256, 0, stream>>>(part, slabs, g, c, c_real, gamma, beta, running_mean,
                                                      running_var, momentum, eps, scale, shift, mean,
                                                      invstd, scratch, counter);
   return cudaGetLastError();
@@ -549,13 +554,14 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
                                 long long z_plane, __nv_bfloat16* dz, long long dz_plane, int planes,
                                 long long rows, int c, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, DropoutCfg drop,
-                                const float* sums, float* dgamma, float* dbeta, cudaStream_t stream) {
+                                const float* sums, float* dgamma, float* dbeta, int c_real,
+                                cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   dim3 grid;
   const RowTiling tl = row_tiling(rows, c, grid);
   bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, dz, dz_plane, planes, rows,
                                                 c, scale, shift, mean, invstd, drop, sums, dgamma,
-                                                dbeta, tl);
+                                                dbeta, c_real, tl);
   return cudaGetLastError();
 }
 

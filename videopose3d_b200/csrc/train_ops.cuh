@@ -33,15 +33,16 @@ constexpr int kReduceCounters = kReduceMaxChannels / 32;  // zero-initialised on
 // part: [slabs][2][c] per-slab sum / sum of squares written by the conv GEMM epilogue (slab s =
 // rows (s%4)*32.. of row tile s/4; geometry as in the GEMM: dilated = per-sample tiles).  Every
 // slab becomes (count, mean, M2) and the slabs are merged in a fixed order (Chan et al.), so the
-// batch variance never forms E[x^2] - E[x]^2 over the whole batch.  Writes scale = gamma*invstd,
+// batch variance never forms E[x^2] - E[x]^2 over the whole batch.  gamma / beta / running_* hold
+// c_real <= c channels; channels [c_real, c) are layout padding and get a zero affine.  Writes scale = gamma*invstd,
 // shift = beta - mean*scale, mean, invstd and updates running_mean / running_var in place
 // (running = (1-m)*running + m*batch, unbiased variance for running_var).
 cudaError_t launch_bn_stats_finalize(const float* part, int slabs, int dilated, int out_rows,
                                      int tiles_per_sample, const float* gamma, const float* beta,
                                      float* running_mean, float* running_var, float momentum,
                                      float eps, float* scale, float* shift, float* mean,
-                                     float* invstd, int c, float* scratch, unsigned* counter,
-                                     cudaStream_t stream);
+                                     float* invstd, int c, int c_real, float* scratch,
+                                     unsigned* counter, cudaStream_t stream);
 
 // out_st[ch] = mul_st[ch] * sum_p sum_f part[p][st][f*c + ch], st < nstat (1 or 2), f < folds, in
 // a fixed order.  part: [n_part][nstat][ld].  mul_st may be null (= 1).
@@ -72,7 +73,8 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
                                 long long z_plane, __nv_bfloat16* dz, long long dz_plane, int planes,
                                 long long rows, int c, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, DropoutCfg drop,
-                                const float* sums, float* dgamma, float* dbeta, cudaStream_t stream);
+                                const float* sums, float* dgamma, float* dbeta, int c_real,
+                                cudaStream_t stream);
 
 // out[c] = sum_rows x[row][c] for fp32 x [rows][c] (shrink.bias gradient), via per-64-row partials
 // summed in a fixed order.
