@@ -81,11 +81,11 @@ def test_plan_create_reports_errors_without_gpu():
     st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
     assert st == -1 and b"odd filter widths" in lib.vp3d_last_error()
     cfg.filter_widths[1] = 3
-    cfg.channels = 100
+    cfg.channels = 0
     st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
-    assert st == -2 and b"multiple of 64" in lib.vp3d_last_error()
+    assert st == -1 and b"channels must be positive" in lib.vp3d_last_error()
+    cfg.channels = 100   # any positive channel count is accepted (padded to 64 internally)
     if not torch.cuda.is_available():
-        cfg.channels = 128
         st = lib.vp3d_plan_create(_capi.ctypes.byref(cfg), _capi.ctypes.byref(h))
         assert st == -3  # VP3D_ERR_CUDA: reported, not a crash and not a CPU fallback
 
