@@ -27,16 +27,18 @@ struct AdamHyper {
 
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float& vmax,
                                             bool amsgrad, const AdamHyper& h) {
-  if (h.weight_decay != 0.0f) g = fmaf(h.weight_decay, p, g);
-  m = m + h.one_minus_beta1 * (g - m);
-  v = v * h.beta2 + (h.one_minus_beta2 * g) * g;
+  // explicit roundings: the plain and the re-packing kernel must produce bit-identical updates, so
+  // nothing is left to the compiler's choice of FMA contraction
+  if (h.weight_decay != 0.0f) g = __fmaf_rn(h.weight_decay, p, g);
+  m = __fmaf_rn(h.one_minus_beta1, __fsub_rn(g, m), m);
+  v = __fmaf_rn(__fmul_rn(h.one_minus_beta2, g), g, __fmul_rn(v, h.beta2));
   float second = v;
   if (amsgrad) {
     vmax = fmaxf(vmax, v);
     second = vmax;
   }
-  const float denom = sqrtf(second) / h.bc2_sqrt + h.eps;
-  p = p - h.step_size * (m / denom);
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(second), h.bc2_sqrt), h.eps);
+  p = __fsub_rn(p, __fmul_rn(h.step_size, __fdiv_rn(m, denom)));
 }
 
 __global__ void __launch_bounds__(kAdamThreads)

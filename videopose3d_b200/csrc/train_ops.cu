@@ -120,18 +120,30 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geo
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
   const int S = gridDim.y;
+  const bool live = ch < c;
   Moments acc = {0.0f, 0.0f, 0.0f};
-  if (ch < c) {
-#pragma unroll 4
-    for (int s = blockIdx.y * 8 + w; s < slabs; s += 8 * S) {
-      const int cnt = slab_count(geom, s);
-      if (cnt == 0) continue;
-      const float sum = __ldg(part + ((size_t)s * 2) * c + ch);
-      const float sq = __ldg(part + ((size_t)s * 2 + 1) * c + ch);
+  // warp w of split y owns the contiguous slab range [lo, hi): loads go out eight slabs at a time
+  // (16 independent requests in flight), the merge stays in ascending slab order
+  const int per = (slabs + 8 * S - 1) / (8 * S);
+  const int lo = (blockIdx.y * 8 + w) * per;
+  const int hi = min(slabs, lo + per);
+  for (int s0 = lo; s0 < hi; s0 += 8) {
+    float sum[8], sq[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = s0 + u;
+      const bool ok = live && s < hi;
+      sum[u] = ok ? __ldg(part + ((size_t)s * 2) * c + ch) : 0.0f;
+      sq[u] = ok ? __ldg(part + ((size_t)s * 2 + 1) * c + ch) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = s0 + u;
+      const int cnt = s < hi ? slab_count(geom, s) : 0;
       Moments b;
       b.n = (float)cnt;
-      b.mean = sum / b.n;
-      b.m2 = fmaxf(fmaf(-sum, b.mean, sq), 0.0f);   // sum (x - mean)^2 inside the 32-row slab
+      b.mean = cnt > 0 ? sum[u] / b.n : 0.0f;
+      b.m2 = fmaxf(fmaf(-sum[u], b.mean, sq[u]), 0.0f);   // sum (x - mean)^2 inside the 32-row slab
       merge(acc, b);
     }
   }
@@ -140,24 +152,39 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geo
   if (w == 0) {
     acc = {sm[0][0][lane], sm[0][1][lane], sm[0][2][lane]};
     for (int k = 1; k < 8; ++k) merge(acc, Moments{sm[k][0][lane], sm[k][1][lane], sm[k][2][lane]});
-    if (S > 1 && ch < c) {
+    if (S > 1 && live) {
       float* o = scratch + ((size_t)blockIdx.y * 3) * c + ch;
       o[0] = acc.n; o[c] = acc.mean; o[2 * (size_t)c] = acc.m2;
     }
   }
   if (S > 1) {
     if (!last_block_of_group(counter, S)) return;
-    if (w != 0) return;
+    // the last block merges the S results: warp w takes splits [w * S/8, ...) in order, then the
+    // warps in order -- the same fixed tree every time
     acc = {0.0f, 0.0f, 0.0f};
-    if (ch < c)
-      for (int y = 0; y < S; ++y) {
-        const float* o = scratch + ((size_t)y * 3) * c + ch;
-        merge(acc, Moments{__ldcg(o), __ldcg(o + c), __ldcg(o + 2 * (size_t)c)});
-      }
+    const int per2 = (S + 7) / 8;
+    float n_[4], m_[4], q_[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int y = w * per2 + u;
+      const bool ok = live && u < per2 && y < S;
+      const float* o = scratch + ((size_t)(ok ? y : 0) * 3) * c + (live ? ch : 0);
+      n_[u] = ok ? __ldcg(o) : 0.0f;
+      m_[u] = ok ? __ldcg(o + c) : 0.0f;
+      q_[u] = ok ? __ldcg(o + 2 * (size_t)c) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) merge(acc, Moments{n_[u], m_[u], q_[u]});
+    __syncthreads();
+    sm[w][0][lane] = acc.n; sm[w][1][lane] = acc.mean; sm[w][2][lane] = acc.m2;
+    __syncthreads();
+    if (w != 0) return;
+    acc = {sm[0][0][lane], sm[0][1][lane], sm[0][2][lane]};
+    for (int k = 1; k < 8; ++k) merge(acc, Moments{sm[k][0][lane], sm[k][1][lane], sm[k][2][lane]});
   } else if (w != 0) {
     return;
   }
-  if (ch >= c) return;
+  if (!live) return;
   if (ch >= c_real) {   // padding channel (channels not a multiple of 64): identically zero
     scale[ch] = 0.0f; shift[ch] = 0.0f; mean_out[ch] = 0.0f; invstd[ch] = 0.0f;
     return;
@@ -191,14 +218,23 @@ ordered_col_sums_kernel(const float* __restrict__ part, int n_part, int nstat, i
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
   const int S = gridDim.y;
+  const bool live = ch < c;
   float a0 = 0.0f, a1 = 0.0f;
-  if (ch < c) {
-    for (int p = blockIdx.y * 8 + w; p < n_part; p += 8 * S) {
-      const float* row = part + (size_t)p * nstat * ld + ch;
-      for (int f = 0; f < folds; ++f) {
-        a0 += __ldg(row + (size_t)f * c);
-        if (nstat == 2) a1 += __ldg(row + ld + (size_t)f * c);
+  const int per = (n_part + 8 * S - 1) / (8 * S);
+  const int lo = (blockIdx.y * 8 + w) * per;
+  const int hi = min(n_part, lo + per);
+  for (int f = 0; f < folds; ++f) {
+    for (int p0 = lo; p0 < hi; p0 += 8) {
+      float x0[8], x1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = live && p0 + u < hi;
+        const float* row = part + (size_t)(ok ? p0 + u : 0) * nstat * ld + (size_t)f * c + (live ? ch : 0);
+        x0[u] = ok ? __ldg(row) : 0.0f;
+        x1[u] = (ok && nstat == 2) ? __ldg(row + ld) : 0.0f;
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a0 += x0[u]; a1 += x1[u]; }
     }
   }
   sm[w][0][lane] = a0; sm[w][1][lane] = a1;
@@ -206,7 +242,7 @@ ordered_col_sums_kernel(const float* __restrict__ part, int n_part, int nstat, i
   if (w == 0) {
     a0 = sm[0][0][lane]; a1 = sm[0][1][lane];
     for (int k = 1; k < 8; ++k) { a0 += sm[k][0][lane]; a1 += sm[k][1][lane]; }
-    if (S > 1 && ch < c) {
+    if (S > 1 && live) {
       scratch[((size_t)blockIdx.y * 2) * c + ch] = a0;
       scratch[((size_t)blockIdx.y * 2 + 1) * c + ch] = a1;
     }
@@ -214,16 +250,20 @@ ordered_col_sums_kernel(const float* __restrict__ part, int n_part, int nstat, i
   if (S > 1) {
     if (!last_block_of_group(counter, S)) return;
     if (w != 0) return;
+    float y0[32], y1[32];
+#pragma unroll
+    for (int y = 0; y < kReduceMaxSplits; ++y) {
+      const bool ok = live && y < S;
+      y0[y] = ok ? __ldcg(scratch + ((size_t)y * 2) * c + ch) : 0.0f;
+      y1[y] = ok ? __ldcg(scratch + ((size_t)y * 2 + 1) * c + ch) : 0.0f;
+    }
     a0 = a1 = 0.0f;
-    if (ch < c)
-      for (int y = 0; y < S; ++y) {
-        a0 += __ldcg(scratch + ((size_t)y * 2) * c + ch);
-        a1 += __ldcg(scratch + ((size_t)y * 2 + 1) * c + ch);
-      }
+#pragma unroll
+    for (int y = 0; y < kReduceMaxSplits; ++y) { a0 += y0[y]; a1 += y1[y]; }
   } else if (w != 0) {
     return;
   }
-  if (ch >= c) return;
+  if (!live) return;
   out0[ch] = mul0 ? a0 * mul0[ch] : a0;
   if (nstat == 2) out1[ch] = mul1 ? a1 * mul1[ch] : a1;
 }
@@ -487,7 +527,7 @@ RowTiling row_tiling(long long rows, int c, dim3& grid, int min_rows = 0) {
 }  // namespace
 
 static int pick_splits(int n_part) {
-  int S = (n_part + 63) / 64;   // ~8 partials per warp
+  int S = (n_part + 127) / 128;   // ~16 partials per warp
   if (S < 1) S = 1;
   if (S > kReduceMaxSplits) S = kReduceMaxSplits;
   return S;

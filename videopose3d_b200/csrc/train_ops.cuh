@@ -25,7 +25,7 @@ struct DropoutCfg {
 };
 
 // Ordered reductions (run-to-run reproducible; no floating-point atomics anywhere in training).
-constexpr int kReduceMaxSplits = 32;      // second-level splits of an ordered reduction
+constexpr int kReduceMaxSplits = 32;      // (the finalize kernel's last-block stage assumes <= 32)      // second-level splits of an ordered reduction
 constexpr int kReduceMaxChannels = 8192;  // scratch: kReduceMaxSplits x 3 x channels floats
 constexpr size_t kReduceScratchFloats = (size_t)kReduceMaxSplits * 3 * kReduceMaxChannels;
 constexpr int kReduceCounters = kReduceMaxChannels / 32;  // zero-initialised once, self-resetting
