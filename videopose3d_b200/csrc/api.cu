@@ -136,17 +136,25 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
                                   : (rows_total + kBlockM - 1) / kBlockM;
     const int cands[3] = {256, 128, 64};
     bool found = false;
+    static int wave_num = 0;   // measurement knob: accept a tile width once it fills 1/wave_num wave
+    if (!wave_num) {
+      const char* e = getenv("VP3D_WAVE_NUM");
+      wave_num = (e && atoi(e) > 0) ? atoi(e) : 2;
+    }
     for (int c : cands) {
       if (d->n_pad % c) continue;
       // half a wave of full-rate 128x256 tiles beats a full wave of narrower (smem-bound) ones
-      if (m_tiles * (d->n_pad / c) * 2 >= num_sms()) { block_n = c; found = true; break; }
+      if (m_tiles * (d->n_pad / c) * wave_num >= num_sms()) { block_n = c; found = true; break; }
     }
     if (!found) block_n = 64;
     // Store blocks that need two auxiliary tiles (hi+lo residual, or residual + the Z tile of the
     // fused BatchNorm backward) only get a second prefetch stage next to 128-wide tiles; those
     // launches are epilogue-bound, so the narrower MMA costs nothing.
+    // (CTA pairs keep 256-wide tiles: their four landing tiles give two-tile blocks two stages)
     const int aux_tiles = (d->res ? (d->res_planes > 0 ? d->res_planes : 1) : 0) + (d->bnb_z ? 1 : 0);
-    if (aux_tiles >= 2 && block_n == 256 && d->n_pad % 128 == 0) block_n = 128;
+    const bool pair_ok = conv_gemm_pairs_enabled() && !(num_sms() & 1) && m_tiles >= 2 &&
+                         (d->out_planes <= 1);
+    if (aux_tiles >= 2 && block_n == 256 && d->n_pad % 128 == 0 && !pair_ok) block_n = 128;
     // (the residual kernel variant has no 256-wide, two-output-plane instantiation)
     if (aux_tiles >= 1 && d->out_planes == 2 && block_n == 256) block_n = 128;
   }
@@ -208,8 +216,9 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     const uint64_t o_samples = d->per_sample_tiles ? d->samples : 1;
     uint64_t o_plane = (uint64_t)d->out_plane_stride;
     if (g.out_planes == 1 || o_plane == 0) o_plane = o_samples * o_rows * o_ld;
+    // (32-row boxes: every epilogue warp stores its own quarter of a tile)
     VP3D_TRY(make_map_4d(&mo, d->out, o_ld, o_rows, o_ld, o_samples, o_rows * o_ld, g.out_planes,
-                         o_plane, kBlockM));
+                         o_plane, 32));
   }
   // Residual through TMA (warp 3 prefetches each 128 x 64 residual tile into shared memory) whenever
   // the residual rows of a tile are one box of a strided row view:

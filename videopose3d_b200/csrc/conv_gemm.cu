@@ -10,8 +10,8 @@
 //                   64-column store blocks of a tile alternate between the groups, so two epilogue
 //                   warps share every SM sub-partition and hide each other's latencies:
 //                   tcgen05.ld -> BN affine / ReLU / residual / batch sums in registers -> bf16 pack
-//                   into the group's SWIZZLE_128B staging tile(s) -> TMA store (coalesced 128-byte
-//                   rows, clipped at the tensor edge by the tensor map)
+//                   into the group's SWIZZLE_128B staging tile(s) -> one TMA store per warp of its
+//                   32 x 64 slice (coalesced 128-byte rows, clipped at the tensor edge by the map)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // PAIR variant (BLOCK_N = 256): the grid is launched in clusters of two CTAs that compute a
@@ -53,7 +53,8 @@ struct GemmCfg {
   // (with two output planes the four staging tiles already take 64 KiB: one auxiliary stage only,
   // the second epilogue group covers the exposed load latency, and the operand pipeline keeps its
   // depth)
-  static constexpr int kResSlots = RES ? (BLOCK_N == 256 ? 3 : 4) : 0;
+  // (CTA pairs stream half the W bytes per stage: a fourth landing tile fits next to 4 stages)
+  static constexpr int kResSlots = RES ? ((BLOCK_N == 256 && !PAIR) ? 3 : 4) : 0;
   static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
   // per-channel affine (scale, shift) of the current N block: 2 x BLOCK_N floats
   static constexpr uint32_t kAffineBytes = 2 * BLOCK_N * 4;
@@ -345,8 +346,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int eg = (warp - 4) >> 2;   // epilogue group 0 / 1
     const int ew = warp & 3;          // TMEM lane quarter this warp may access
     const int r_in_tile = ew * 32 + lane;
-    const bool store_leader = (threadIdx.x == 128u + 128u * eg);
-    const uint32_t bar_id = 1 + eg;
     uint32_t acc = 0, acc_phase = 0;
     uint32_t gblock = 0;              // store blocks seen so far (both groups count all of them)
     uint32_t ablock = 0;              // auxiliary stages seen so far
@@ -531,11 +530,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             }
             if (half == 0) {
-              // This group's staging tile(s) must have been read out by the bulk store that used
-              // them last (two store blocks ago).  The wait sits after the TMEM load and the math
+              // This warp's 32 rows of the group's staging tile(s) must have been read out by the
+              // bulk store it issued from them (two store blocks ago).  Every warp stores its own
+              // 32 x 64 box, so nothing but the warp itself has to be waited for: no CTA-level
+              // barrier sits in the store path.  The wait comes after the TMEM load and the math
               // of this chunk so that store latency overlaps that work.
-              if (store_leader) tma_store_wait_read<0>();
-              group_bar_sync(bar_id);
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -557,11 +558,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (half == 1) {
               fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
-              group_bar_sync(bar_id);
-              if (store_leader) {
-                tma_store_4d(&tmap_out, my_store, cb, row0, sample, 0);
+              __syncwarp();
+              if (lane == 0) {
+                // rows [32 ew, 32 ew + 32) of the staging tile: a 1024-byte aligned slice, so the
+                // 128-byte swizzle pattern of the 32-row box matches the one the tile was written in
+                const uint32_t src = my_store + (uint32_t)ew * 32u * 128u;
+                tma_store_4d(&tmap_out, src, cb, row0 + ew * 32, sample, 0);
                 if (two_planes_t)
-                  tma_store_4d(&tmap_out, my_store + Cfg::kTileBytes, cb, row0, sample, 1);
+                  tma_store_4d(&tmap_out, src + Cfg::kTileBytes, cb, row0 + ew * 32, sample, 1);
                 tma_store_commit();
               }
             }
@@ -667,7 +671,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     // the staging tiles must outlive every bulk store that reads them
-    if (store_leader) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   __syncwarp();
@@ -704,6 +708,8 @@ static bool pair_enabled() {
   }
   return v != 0;
 }
+
+bool conv_gemm_pairs_enabled() { return pair_enabled(); }
 
 template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,

@@ -100,7 +100,7 @@ struct ConvGemmArgs {
 };
 
 // Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);
-// tmap_out: 4-D (channel, row, sample, plane) over the bf16 output, box (64, 128, 1, 1) (ignored —
+// tmap_out: 4-D (channel, row, sample, plane) over the bf16 output, box (64, 32, 1, 1) (ignored —
 // pass any valid map — when the launch writes fp32).
 // tmap_res: 4-D (channel, row, sample, plane) over the residual's row view, box (64, 128, 1, 1); used
 // only when args.res_tma is set.
@@ -108,6 +108,7 @@ struct ConvGemmArgs {
 // tmap_w: box rows = block_n, or block_n / 2 when conv_gemm_uses_pair() says the launch runs on CTA
 // pairs (each CTA of a pair loads its half of the N block).
 bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms);
+bool conv_gemm_pairs_enabled();   // VP3D_PAIR != 0
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
