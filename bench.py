@@ -161,6 +161,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` BEFORE the pinned
+    host buffers are allocated (first touch places them on that NUMA node): host->device copies
+    from the far socket ran at half the PCIe rate on some boxes.  Returns the previous affinity
+    (to restore for the CPU baseline) or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        new = cpus & old
+        if not new or new == old:
+            return None
+        os.sched_setaffinity(0, new)
+        return old
+    except Exception:
+        return None
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask and cgroup CPU quota, not just the
     machine's logical CPU count (a 128-thread pool on a quota of a few cores crawls)."""
@@ -388,20 +410,27 @@ def measure_train(dev, rank, world, steps, warmup, n_seq, compress=None):
         return loss
 
     def timed(n):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        """(device ms/step with the launch queue kept full, wall ms/step when the loss is read back
+        every step as run.py:414 does, last loss)."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for a, b in evs:
-            a.record()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
             loss = step()
-            b.record()
-            loss.item()                       # run.py:414 reads the loss every step
+        b.record()
+        torch.cuda.synchronize()
+        gpu_ms = a.elapsed_time(b) / n
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            loss = step()
+            last = loss.item()                # run.py:414 reads the loss every step
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        gpu_ms = sum(a.elapsed_time(b) for a, b in evs) / n
-        return gpu_ms, wall / n * 1e3, float(loss)
+        return gpu_ms, wall / n * 1e3, float(last)
 
     out = {}
     if world > 1:
@@ -438,7 +467,9 @@ def measure_train(dev, rank, world, steps, warmup, n_seq, compress=None):
         "frac_of_bf16_peak_burst": tf / peak_tf, "frac_of_bf16_peak_sustained": tf / sustained,
         "dtype": "bf16 operands, fp32 accumulate / statistics / master weights",
         "steps": steps, "last_loss": last_loss, "h2d_bytes_per_step": 0,
-        "timing": "CUDA events per step (max over ranks); the step's working set (~1 GB) exceeds L2",
+        "timing": "ms_per_step: CUDA events around `steps` back-to-back steps (launch queue full, max "
+                  "over ranks); ms_per_step_wall_incl_loss_item: host clock with loss.item() after "
+                  "every step as run.py does; the step's working set (~1 GB) exceeds L2",
     })
     if world > 1:
         grad_bytes = sum(p.numel() for p in model.parameters()) * (2 if compress == "bf16" else 4)
@@ -558,6 +589,7 @@ def run_ours(args, rank, local_rank, world):
         dom_ms = ms.value / max(cnt.value, 1)
 
         # ---------------- end-to-end through the host-buffer API
+        old_affinity = bind_to_gpu_numa_node(_visible_index(local_rank))
         xh = [orc.make_input(N_PER_GPU, T, J, F, seed=500 + rank * 2 + i).pin_memory() for i in range(2)]
         yh = torch.empty((N_PER_GPU, 1, J, 3), dtype=torch.float32).pin_memory()
         for i in range(max(3, args.warmup // 4)):
@@ -588,6 +620,8 @@ def run_ours(args, rank, local_rank, world):
         for i in range(max(0, e2e_steps - 2), e2e_steps):
             model.forward_host_wait(i & 1)
         e2e_s = time.perf_counter() - t0
+        if old_affinity is not None:
+            os.sched_setaffinity(0, old_affinity)
 
     # max over ranks
     if world > 1:
@@ -679,6 +713,9 @@ def run_ours(args, rank, local_rank, world):
                     "api": "TemporalModel.forward_host_submit/_wait -> vp3d_forward_eval_host_submit/"
                            "_wait (pinned host buffers, two slots: copy-in of step i+1 overlaps the "
                            "kernels of step i)",
+                    "host_numa_binding": "process bound to the GPU-local cores (NVML) while the pinned "
+                                         "buffers were allocated and the copies issued"
+                                         if old_affinity is not None else "none (already local / unavailable)",
                     "sync_call_ms_per_step": e2e_sync_s / e2e_steps * 1e3,
                     "sync_call_value": N_PER_GPU * e2e_steps / e2e_sync_s},
             "gpu_launches": launches_per_step * args.steps,

@@ -14,7 +14,7 @@ outputs, every loss term, d(total)/d(model outputs) and every parameter gradient
 distortion-aware and the linear projection.
 
 `big_opt_33333_c1024_train.npz` -- TemporalModelOptimized1f arc 3,3,3,3,3, C = 1024 (the cfg3 shape),
-N = 128 windows, train mode, dropout 0: output, updated running statistics and the gradient of every
+N = 1024 windows (the full cfg3 batch), train mode, dropout 0: output, updated running statistics and the gradient of every
 parameter; the 9 conv-weight gradients (up to 3.1 M elements each) are stored as a strided sample
 of 4096 entries + their L2 norm + their sum, parameters are regenerated from the seed.
 
@@ -158,7 +158,7 @@ def sample_idx(numel):
 
 
 def cfg3_train_case():
-    arc, C, J, N, T, seed, momentum = [3, 3, 3, 3, 3], 1024, 17, 128, 243, 4321, 0.1
+    arc, C, J, N, T, seed, momentum = [3, 3, 3, 3, 3], 1024, 17, 1024, 243, 4321, 0.1
     sd = orc.make_state_dict(J, 2, J, arc, C, seed=seed)
     x = orc.make_input(N, T, J, 2, seed=seed + 1)
     model = TemporalModelOptimized1f(J, 2, J, filter_widths=arc, dropout=0.0, channels=C)
