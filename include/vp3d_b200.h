@@ -83,6 +83,10 @@ typedef struct vp3d_plan vp3d_plan;
 
 int vp3d_version(void);
 const char* vp3d_last_error(void);
+/* Cap the persistent grids of the GEMM kernels at n SMs (0 = all): a data-parallel host leaves the
+ * remaining SMs to the NCCL kernels of an overlapped gradient all-reduce, which otherwise cannot be
+ * scheduled next to one-CTA-per-SM grids (no reference counterpart: the reference is single-GPU). */
+int vp3d_set_sm_limit(int n);
 
 /* Replaces TemporalModel.__init__ / TemporalModelOptimized1f.__init__ (model.py:85-124, 151-185):
  * validates odd filter widths, derives pad / causal_shift / dilation per block, allocates the packed

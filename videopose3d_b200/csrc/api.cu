@@ -98,6 +98,7 @@ int pick_block_n(int n_pad) {
 }
 
 // SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
+static int g_sm_limit = 0;   // vp3d_set_sm_limit: persistent grids leave the other SMs to NCCL
 int num_sms() {
   static int cache[kMaxDevices] = {};
   int dev = 0;
@@ -106,12 +107,32 @@ int num_sms() {
     int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cache[dev] = n > 0 ? n : 148;
+    if (const char* e = getenv("VP3D_SM_LIMIT")) {
+      const int lim = atoi(e);
+      if (lim >= 2 && !g_sm_limit) g_sm_limit = lim;
+    }
   }
-  return cache[dev];
+  int n = cache[dev];
+  if (g_sm_limit >= 2 && g_sm_limit < n) n = g_sm_limit & ~1;   // even: CTA pairs
+  return n;
 }
 
 // ------------------------------------------------------------------ operator level
-int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
+static bool xpack_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VP3D_XPACK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) { return run_conv_x(d, stream, nullptr); }
+
+// `xp` (optional): how to build the A operand from the network's fp32 input.  If the launch can
+// run the variant that does so in-kernel it does (xp->fused = 1); otherwise the separate pack
+// kernel fills d->a first (xp->fused = 0).
+int run_conv_x(const vp3d_conv_desc* d, cudaStream_t stream, XpackInfo* xp) {
   if (!d || !d->a || !d->w) return fail(VP3D_ERR_INVALID, "conv_gemm: null operand");
   if (d->a_ld % 64 || d->k_per_tap % 64 || d->n_pad % 64)
     return fail(VP3D_ERR_INVALID, "conv_gemm: a_ld, k_per_tap and n_pad must be multiples of 64");
@@ -280,6 +301,26 @@ int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
     g.bnb_seed_hi = (unsigned)(d->bnb_seed >> 32);
     g.bnb_layer = (unsigned)d->bnb_layer;
   }
+  if (xp) {
+    xp->fused = 0;
+    const bool can = xpack_enabled() && a_planes == 1 && !d->per_sample_tiles && d->taps == 1 &&
+                     (xp->c_raw % 2 == 0) && (reinterpret_cast<uintptr_t>(xp->x) % 8 == 0) &&
+                     !d->stats && !d->out_f32 && g.out_planes == 1 && !d->res &&
+                     xp->perm.levels <= 8 && conv_gemm_uses_wres(g, block_n, num_sms());
+    if (can) {
+      g.xsrc = xp->x; g.x_T = xp->T; g.x_c_raw = xp->c_raw; g.x_k_valid = xp->group * xp->c_raw;
+      g.x_frame_step = xp->frame_step;
+      g.perm_levels = xp->perm.levels; g.perm_last_rows = xp->perm.last_rows;
+      for (int i = 0; i < 8; ++i) { g.perm_region[i] = xp->perm.region[i]; g.perm_width[i] = xp->perm.width[i]; }
+      if (g.perm_levels == 0) g.perm_last_rows = d->out_rows / (xp->N > 0 ? xp->N : 1);
+      xp->fused = 1;
+    } else {
+      CUDA_TRY(launch_pack_input(xp->x, static_cast<__nv_bfloat16*>(const_cast<void*>(d->a)), a_planes,
+                                 xp->N, xp->T, xp->c_raw, xp->rows, xp->group, xp->frame_step,
+                                 (int)d->a_ld, (long long)plane_stride, stream,
+                                 xp->perm.levels ? &xp->perm : nullptr, f16));
+    }
+  }
   // W boxes: the whole N block, or half of it per CTA when the launch runs on CTA pairs
   const bool pair = conv_gemm_uses_pair(g, block_n, num_sms());
   VP3D_TRY(make_map_2d(&mw, d->w, d->k_per_tap, (uint64_t)w_planes * d->taps * d->n_pad,
@@ -311,6 +352,11 @@ static int alloc_packed(vp3d_plan* p, PackedConv& pc, int taps, int k_per_tap, i
 }
 
 extern "C" __attribute__((visibility("default"))) int vp3d_version(void) { return VP3D_VERSION; }
+extern "C" __attribute__((visibility("default"))) int vp3d_set_sm_limit(int n) {
+  if (n != 0 && n < 2) return fail(VP3D_ERR_INVALID, "set_sm_limit: need 0 (no limit) or >= 2 SMs");
+  vp3d::g_sm_limit = n;
+  return VP3D_OK;
+}
 extern "C" __attribute__((visibility("default"))) const char* vp3d_last_error(void) { return g_err; }
 
 extern "C" __attribute__((visibility("default"))) int vp3d_plan_create(const vp3d_config* cfg, vp3d_plan** out_plan) {
@@ -662,6 +708,9 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   // region.  Only that region of X needs the lo plane in `mixed` mode.
   long long R[VP3D_MAX_WIDTHS];
   for (int i = 0; i <= p->nb; ++i) R[i] = (long long)N * L[i];
+  XpackInfo xpack;
+  memset(&xpack, 0, sizeof(xpack));
+  bool use_xpack = false;
   auto lo_rows = [&](int i, vp3d_conv_desc& q) {  // q produces X_i
     q.lo_row_begin = 0;
     q.lo_row_end = 0;  // every row
@@ -681,8 +730,9 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       perm.region[i - 1] = (unsigned)R[i];
       perm.width[i - 1] = fw[i];
     }
-    VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
-                               (long long)wl.a0_plane, stream, &perm, p->f16)));
+    xpack.x = x; xpack.N = N; xpack.T = T; xpack.c_raw = p->c_in_raw; xpack.rows = L[0];
+    xpack.group = fw[0]; xpack.frame_step = fw[0]; xpack.perm = perm;
+    use_xpack = true;
     common(d, x3[0]);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
@@ -698,7 +748,15 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   d.scale = p->expand_dil.scale; d.shift = p->expand_dil.shift; d.relu = 1;
   d.out = xb[0]; d.out_plane_stride = (long long)wl.x_plane; d.out_ld = C;
   lo_rows(0, d);
-  VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
+  if (use_xpack) {
+    // input packing either happens inside the expand GEMM (one launch) or as its own kernel first
+    VP3D_TRY(prof_event(true));
+    VP3D_TRY(run_conv_x(&d, stream, &xpack));
+    VP3D_TRY(prof_event(false));
+    launches += xpack.fused ? 1 : 2;
+  } else {
+    VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
+  }
 
   // ---- residual blocks (model.py:129-135 / :190-194)
   int cur = 0;
