@@ -87,6 +87,11 @@ const char* vp3d_last_error(void);
  * remaining SMs to the NCCL kernels of an overlapped gradient all-reduce, which otherwise cannot be
  * scheduled next to one-CTA-per-SM grids (no reference counterpart: the reference is single-GPU). */
 int vp3d_set_sm_limit(int n);
+/* Programmatic dependent launch of the GEMM kernels (on by default: the next kernel's prologue
+ * overlaps the tail of the current one).  A host that overlaps NCCL collectives with the backward
+ * turns it off: gap-free hand-over between one-CTA-per-SM grids starves the NCCL kernels of SMs
+ * (measured: 2-GPU step 2.76 ms with it off, tens of ms per synchronised step with it on). */
+int vp3d_set_pdl(int on);
 
 /* Replaces TemporalModel.__init__ / TemporalModelOptimized1f.__init__ (model.py:85-124, 151-185):
  * validates odd filter widths, derives pad / causal_shift / dilation per block, allocates the packed

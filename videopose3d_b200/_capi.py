@@ -153,6 +153,7 @@ SIGNATURES = {
     "vp3d_version": (ctypes.c_int, []),
     "vp3d_last_error": (ctypes.c_char_p, []),
     "vp3d_set_sm_limit": (ctypes.c_int, [ctypes.c_int]),
+    "vp3d_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "vp3d_plan_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(ctypes.c_void_p)]),
     "vp3d_plan_destroy": (None, [ctypes.c_void_p]),
     "vp3d_receptive_field": (ctypes.c_int, [ctypes.c_void_p]),

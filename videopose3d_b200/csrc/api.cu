@@ -352,6 +352,10 @@ static int alloc_packed(vp3d_plan* p, PackedConv& pc, int taps, int k_per_tap, i
 }
 
 extern "C" __attribute__((visibility("default"))) int vp3d_version(void) { return VP3D_VERSION; }
+extern "C" __attribute__((visibility("default"))) int vp3d_set_pdl(int on) {
+  vp3d::conv_gemm_set_pdl(on);
+  return VP3D_OK;
+}
 extern "C" __attribute__((visibility("default"))) int vp3d_set_sm_limit(int n) {
   if (n != 0 && n < 2) return fail(VP3D_ERR_INVALID, "set_sm_limit: need 0 (no limit) or >= 2 SMs");
   vp3d::g_sm_limit = n;

@@ -767,14 +767,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // stream may start its prologue (barrier init, TMEM allocation, descriptor prefetch) on SMs this
 // grid has already left; its griddepcontrol.wait still orders every global access behind the
 // completion of this grid.
+static int g_pdl = -1;   // -1: not decided yet (VP3D_PDL, default on); conv_gemm_set_pdl overrides
 static bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("VP3D_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
   }
-  return v != 0;
+  return g_pdl != 0;
 }
+void conv_gemm_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 // CTA pairs (cta_group::2) for the 256-wide streamed-W launches: VP3D_PAIR=0 turns them off.
 static bool pair_enabled() {

@@ -120,6 +120,7 @@ bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms);
 // Whether the launch runs the W-resident variant (the only one that can build A from fp32 input).
 bool conv_gemm_uses_wres(const ConvGemmArgs& args, int block_n, int num_sms);
 bool conv_gemm_pairs_enabled();   // VP3D_PAIR != 0
+void conv_gemm_set_pdl(int on);   // programmatic dependent launch of the GEMM kernels (default on)
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
