@@ -118,21 +118,7 @@ int num_sms() {
 }
 
 // ------------------------------------------------------------------ operator level
-static bool xpack_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VP3D_XPACK");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
-}
-
-int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) { return run_conv_x(d, stream, nullptr); }
-
-// `xp` (optional): how to build the A operand from the network's fp32 input.  If the launch can
-// run the variant that does so in-kernel it does (xp->fused = 1); otherwise the separate pack
-// kernel fills d->a first (xp->fused = 0).
-int run_conv_x(const vp3d_conv_desc* d, cudaStream_t stream, XpackInfo* xp) {
+int run_conv(const vp3d_conv_desc* d, cudaStream_t stream) {
   if (!d || !d->a || !d->w) return fail(VP3D_ERR_INVALID, "conv_gemm: null operand");
   if (d->a_ld % 64 || d->k_per_tap % 64 || d->n_pad % 64)
     return fail(VP3D_ERR_INVALID, "conv_gemm: a_ld, k_per_tap and n_pad must be multiples of 64");
@@ -300,26 +286,6 @@ int run_conv_x(const vp3d_conv_desc* d, cudaStream_t stream, XpackInfo* xp) {
     g.bnb_seed_lo = (unsigned)(d->bnb_seed & 0xFFFFFFFFu);
     g.bnb_seed_hi = (unsigned)(d->bnb_seed >> 32);
     g.bnb_layer = (unsigned)d->bnb_layer;
-  }
-  if (xp) {
-    xp->fused = 0;
-    const bool can = xpack_enabled() && a_planes == 1 && !d->per_sample_tiles && d->taps == 1 &&
-                     (xp->c_raw % 2 == 0) && (reinterpret_cast<uintptr_t>(xp->x) % 8 == 0) &&
-                     !d->stats && !d->out_f32 && g.out_planes == 1 && !d->res &&
-                     xp->perm.levels <= 8 && conv_gemm_uses_wres(g, block_n, num_sms());
-    if (can) {
-      g.xsrc = xp->x; g.x_T = xp->T; g.x_c_raw = xp->c_raw; g.x_k_valid = xp->group * xp->c_raw;
-      g.x_frame_step = xp->frame_step;
-      g.perm_levels = xp->perm.levels; g.perm_last_rows = xp->perm.last_rows;
-      for (int i = 0; i < 8; ++i) { g.perm_region[i] = xp->perm.region[i]; g.perm_width[i] = xp->perm.width[i]; }
-      if (g.perm_levels == 0) g.perm_last_rows = d->out_rows / (xp->N > 0 ? xp->N : 1);
-      xp->fused = 1;
-    } else {
-      CUDA_TRY(launch_pack_input(xp->x, static_cast<__nv_bfloat16*>(const_cast<void*>(d->a)), a_planes,
-                                 xp->N, xp->T, xp->c_raw, xp->rows, xp->group, xp->frame_step,
-                                 (int)d->a_ld, (long long)plane_stride, stream,
-                                 xp->perm.levels ? &xp->perm : nullptr, f16));
-    }
   }
   // W boxes: the whole N block, or half of it per CTA when the launch runs on CTA pairs
   const bool pair = conv_gemm_uses_pair(g, block_n, num_sms());
@@ -712,9 +678,6 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   // region.  Only that region of X needs the lo plane in `mixed` mode.
   long long R[VP3D_MAX_WIDTHS];
   for (int i = 0; i <= p->nb; ++i) R[i] = (long long)N * L[i];
-  XpackInfo xpack;
-  memset(&xpack, 0, sizeof(xpack));
-  bool use_xpack = false;
   auto lo_rows = [&](int i, vp3d_conv_desc& q) {  // q produces X_i
     q.lo_row_begin = 0;
     q.lo_row_end = 0;  // every row
@@ -734,9 +697,8 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
       perm.region[i - 1] = (unsigned)R[i];
       perm.width[i - 1] = fw[i];
     }
-    xpack.x = x; xpack.N = N; xpack.T = T; xpack.c_raw = p->c_in_raw; xpack.rows = L[0];
-    xpack.group = fw[0]; xpack.frame_step = fw[0]; xpack.perm = perm;
-    use_xpack = true;
+    VP3D_LAUNCH(CUDA_TRY(launch_pack_input(x, a0, p->planes, N, T, p->c_in_raw, L[0], fw[0], fw[0], p->k0_pad,
+                               (long long)wl.a0_plane, stream, &perm, p->f16)));
     common(d, x3[0]);
     d.a = a0; d.samples = 1; d.a_rows = N * L[0]; d.a_ld = p->k0_pad;
     d.w = p->expand_flat.w; d.taps = 1; d.k_per_tap = p->k0_pad; d.n_pad = C;
@@ -752,15 +714,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_forward_eval(vp3d_pla
   d.scale = p->expand_dil.scale; d.shift = p->expand_dil.shift; d.relu = 1;
   d.out = xb[0]; d.out_plane_stride = (long long)wl.x_plane; d.out_ld = C;
   lo_rows(0, d);
-  if (use_xpack) {
-    // input packing either happens inside the expand GEMM (one launch) or as its own kernel first
-    VP3D_TRY(prof_event(true));
-    VP3D_TRY(run_conv_x(&d, stream, &xpack));
-    VP3D_TRY(prof_event(false));
-    launches += xpack.fused ? 1 : 2;
-  } else {
-    VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
-  }
+  VP3D_LAUNCH(VP3D_TRY(run_conv(&d, stream)));
 
   // ---- residual blocks (model.py:129-135 / :190-194)
   int cur = 0;

@@ -126,10 +126,7 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
 
 // TRAIN compiles in the training-only epilogue paths (BatchNorm batch statistics of the stored
 // value, fused BatchNorm-backward reductions); eval launches use the leaner TRAIN = false build.
-// XPACK (W-resident, eval): warps 0 and 3 build the A tiles in shared memory straight from the
-// network's fp32 input (tap-major gather + fp16 / bf16 conversion + 128-byte swizzle), replacing the
-// separate pack kernel and the round trip of the packed copy through HBM.
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR, bool XPACK>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
@@ -197,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar + s * 8, XPACK ? 64 : 1);   // XPACK: the 64 threads that write the A tile
+      mbar_init(full_bar + s * 8, 1);
       mbar_init(empty_bar + s * 8, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -228,81 +225,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   griddep_wait();
   griddep_launch_dependents();
 
-  if (XPACK && (warp == 0 || warp == 3)) {
-    // ------------------------------------------------------------ A-tile builder (64 threads)
-    static_assert(!XPACK || (WRES && !PAIR && !RES), "XPACK is a W-resident, single-CTA variant");
-    if (warp == 0 && lane == 0) {
-      // the resident W slab of this CTA's N block, once (same as the TMA producer below)
-      const int n_blk = blockIdx.x % p.n_tiles;
-      const int w_tiles = p.taps * p.kblocks_per_tap;
-      mbar_expect_tx(wfull_bar, w_tiles * Cfg::kBBytes);
-      for (int wi = 0; wi < w_tiles; ++wi)
-        tma_load_2d(&tmap_w, wfull_bar, smem_b + wi * Cfg::kBBytes, (wi % p.kblocks_per_tap) * kBlockK,
-                    (wi / p.kblocks_per_tap) * p.n_pad + n_blk * BLOCK_N);
-    }
-    __syncwarp();
-    const int q = (warp == 0 ? 0 : 32) + lane;   // rows q and q + 64 of every tile
-    const bool f16 = p.f16 != 0;
-    uint32_t stage = 0, phase = 0;
-    for (int w = worker; w < total_tiles; w += num_workers) {
-      int n_blk, sample, row0;
-      tile_coords(p, tile_of(w), n_blk, sample, row0);
-      const float* src[2];
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = row0 + q + 64 * rr;
-        src[rr] = nullptr;
-        if (row < p.out_rows) {
-          unsigned j = (unsigned)row;
-          int frame = 0, weight = 1;
-          for (int lv = 0; lv < p.perm_levels; ++lv) {
-            const unsigned dgt = j / p.perm_region[lv];
-            j -= dgt * p.perm_region[lv];
-            frame += (int)dgt * weight;
-            weight *= p.perm_width[lv];
-          }
-          const int n = (int)(j / (unsigned)p.perm_last_rows);
-          const int r = frame + (int)(j - (unsigned)n * (unsigned)p.perm_last_rows) * weight;
-          src[rr] = p.xsrc + ((long long)n * p.x_T + (long long)r * p.x_frame_step) * p.x_c_raw;
-        }
-      }
-      for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-        mbar_wait(empty_bar + stage * 8, phase ^ 1);
-        const uint32_t tile_base = smem_a + stage * Cfg::kABytes;
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r_in_tile = q + 64 * rr;
-          const uint32_t dst = tile_base + r_in_tile * 128;
-          const uint32_t sw = r_in_tile & 7;
-          const float* s0 = src[rr];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {          // 8 chunks of 8 elements (16 bytes) per 64-column row
-            const int k0 = kb * kBlockK + c * 8;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {     // rows start 8-byte aligned (c_raw even): float2 loads
-              float2 t = make_float2(0.0f, 0.0f);
-              if (s0 != nullptr && k0 + e + 1 < p.x_k_valid) {
-                t = __ldg(reinterpret_cast<const float2*>(s0 + k0 + e));
-              } else if (s0 != nullptr && k0 + e < p.x_k_valid) {
-                t.x = __ldg(s0 + k0 + e);
-              }
-              v[e] = t.x;
-              v[e + 1] = t.y;
-            }
-            uint32_t u[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              u[e] = f16 ? pack_f16x2(v[2 * e], v[2 * e + 1]) : pack_bf16x2(v[2 * e], v[2 * e + 1]);
-            st_shared_v4(dst + (((uint32_t)c ^ sw) << 4), u[0], u[1], u[2], u[3]);
-          }
-        }
-        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's reads
-        mbar_arrive(full_bar + stage * 8);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -789,13 +712,13 @@ static bool pair_enabled() {
 
 bool conv_gemm_pairs_enabled() { return pair_enabled(); }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR, bool XPACK = false>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN, PAIR, XPACK>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN, PAIR>;
   // the dynamic shared memory opt-in is a per-device attribute
   static bool attr_set[kMaxDevices] = {};
   int dev = 0;
@@ -884,15 +807,6 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
                              int num_sms, cudaStream_t stream) {
   const bool res = args.res_tma != 0 || args.bnb != 0;
   const bool wres = conv_gemm_uses_wres(args, block_n, num_sms);
-  if (args.xsrc) {
-    // A built in-kernel from fp32 input: W-resident, single-plane, inference-epilogue launches only
-    const bool plain = wres && args.pairs == 1 && !(args.flags & (kEpiStats | kEpiOutF32)) &&
-                       !(args.out_planes == 2) && !args.dilated;
-    if (!plain) return cudaErrorInvalidConfiguration;
-    if (block_n == 256)
-      return launch_impl<256, false, true, false, false, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
-    return launch_impl<128, false, true, false, false, false, true>(tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args, num_sms, stream);
-  }
   switch (block_n) {
     case 256:
       if (conv_gemm_uses_pair(args, block_n, num_sms)) {

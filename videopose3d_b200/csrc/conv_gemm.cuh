@@ -97,15 +97,6 @@ struct ConvGemmArgs {
   // two output planes: the lo plane is only produced for tiles that intersect rows
   // [lo_row_begin, lo_row_end) (flat tiling; the rows a later residual add / split-bf16 GEMM reads)
   int lo_row_begin, lo_row_end;
-  // ---- XPACK (expand conv of the eval cone schedule): the A operand is built inside the kernel
-  // from the network's fp32 input instead of being TMA-loaded from a packed copy.  Row `row` of the
-  // GEMM gathers x_k_valid consecutive floats of sample n starting at frame r * x_frame_step, with
-  // (n, r) the tap-major permutation of `row` (pack.cuh); columns >= x_k_valid are zero.
-  const float* xsrc;   // (N, T, c_raw) fp32, or null (A comes through tmap_a)
-  int x_T, x_c_raw, x_k_valid, x_frame_step;
-  int perm_levels, perm_last_rows;
-  unsigned perm_region[8];
-  int perm_width[8];
 };
 
 // Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);
@@ -117,7 +108,7 @@ struct ConvGemmArgs {
 // tmap_w: box rows = block_n, or block_n / 2 when conv_gemm_uses_pair() says the launch runs on CTA
 // pairs (each CTA of a pair loads its half of the N block).
 bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms);
-// Whether the launch runs the W-resident variant (the only one that can build A from fp32 input).
+// Whether the launch runs the W-resident variant.
 bool conv_gemm_uses_wres(const ConvGemmArgs& args, int block_n, int num_sms);
 bool conv_gemm_pairs_enabled();   // VP3D_PAIR != 0
 void conv_gemm_set_pdl(int on);   // programmatic dependent launch of the GEMM kernels (default on)

@@ -40,17 +40,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int num_sms();
 int run_conv(const vp3d_conv_desc* d, cudaStream_t stream);
-struct XpackInfo;
-int run_conv_x(const vp3d_conv_desc* d, cudaStream_t stream, XpackInfo* xp);
 
-// Recipe for the A operand of the expand conv: rows gathered from the fp32 network input
-// (see launch_pack_input); run_conv_x reports in `fused` whether the GEMM built them itself.
-struct XpackInfo {
-  const float* x;
-  int N, T, c_raw, rows, group, frame_step;
-  PackPerm perm;
-  int fused;
-};
 
 struct PackedConv {
   __nv_bfloat16* w = nullptr;
