@@ -437,12 +437,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (aux_here) ++ablock;
         if ((gblock & 1u) != (uint32_t)eg) continue;  // the other group owns this store block
 
-#pragma unroll 1
+        // Inference launches without auxiliary tiles have the registers to fetch BOTH 32-column
+        // halves of the store block up front: one exposed TMEM round trip per block instead of two,
+        // and the second half's load overlaps the first half's math.
+        constexpr bool kPreload = !RES && !TRAIN;
+        uint32_t pre[kPreload ? 2 : 1][32];
+        if (kPreload) {
+          tmem_ld_32x32(t_addr + (sb * 2) * 32, pre[0]);
+          tmem_ld_32x32(t_addr + (sb * 2 + 1) * 32, pre[kPreload ? 1 : 0]);
+          tmem_ld_wait();
+          if (sb == last_owned) {
+            tc_fence_before();
+            if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+          }
+        }
+#pragma unroll (kPreload ? 2 : 1)
         for (int half = 0; half < 2; ++half) {
           const int chunk = sb * 2 + half;
           const int c0 = cb + half * 32;
           uint32_t raw[32];
-          tmem_ld_32x32(t_addr + chunk * 32, raw);
+          if (kPreload) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = pre[kPreload ? half : 0][j];
+          } else {
+            tmem_ld_32x32(t_addr + chunk * 32, raw);
+          }
           // while the TMEM load is in flight: make sure the auxiliary tiles of this block have
           // landed and fetch this row's residual bytes (plane 0) from shared memory
           uint4 rres[4];
@@ -460,11 +479,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int q = 0; q < 4; ++q) rres[q] = ld_shared_v4(src + (((half * 4 + q) ^ sw) << 4));
             }
           }
-          tmem_ld_wait();
-          if (sb == last_owned && half == 1) {
-            // every accumulator column this thread needs from the tile is in registers
-            tc_fence_before();
-            if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+          if (!kPreload) {
+            tmem_ld_wait();
+            if (sb == last_owned && half == 1) {
+              // every accumulator column this thread needs from the tile is in registers
+              tc_fence_before();
+              if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+            }
           }
           float v[32];
 #pragma unroll
