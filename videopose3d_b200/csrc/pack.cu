@@ -20,62 +20,63 @@ __device__ __forceinline__ __nv_bfloat16 f16_bits(float v) {
   return __ushort_as_bfloat16(h);
 }
 
-// One thread per (row, 8-column group): 16-byte stores, coalesced along the row.  The source row of
-// an output row (sample, first frame: up to six integer divisions in the tap-major order) is
-// computed once per row by the thread of column group 0 and shared through shared memory.
-__global__ void __launch_bounds__(256)
-pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int planes, int N,
-                  int T, int c_raw, int rows, int group, int frame_step, int k_pad,
-                  long long plane_stride, const PackPerm perm, int f16) {
-  __shared__ long long s_src[256];
-  const int groups_per_row = k_pad >> 3;                 // <= 256 (k_pad <= 2048)
-  const int rows_per_block = 256 / groups_per_row;       // >= 1
-  const int g = threadIdx.x % groups_per_row;
-  const int rl = threadIdx.x / groups_per_row;
-  const long long total_rows = (long long)N * rows;
+// One thread per (row, 8-column group): 16-byte stores, coalesced along the row.
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                  int planes, int N, int T, int c_raw, int rows, int group,
+                                  int frame_step, int k_pad, long long plane_stride,
+                                  const PackPerm perm, int f16) {
+  const int groups_per_row = k_pad >> 3;
+  const long long total = (long long)N * rows * groups_per_row;
   const int k_valid = group * c_raw;
-  for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < total_rows;
-       row0 += (long long)gridDim.x * rows_per_block) {
-    const long long row = row0 + rl;
-    const bool live = rl < rows_per_block && row < total_rows;
-    if (live && g == 0) {
-      long long n, r;
-      if (perm.levels == 0) {
-        n = row / rows;
-        r = row - n * rows;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int g;
+    long long row;
+    if (total < 0x7fffffffll) {  // 32-bit index math (the common case): far cheaper divisions
+      const unsigned iu = (unsigned)i;
+      const unsigned ru = iu / (unsigned)groups_per_row;
+      g = (int)(iu - ru * (unsigned)groups_per_row);
+      row = ru;
+    } else {
+      g = (int)(i % groups_per_row);
+      row = i / groups_per_row;
+    }
+    int r, n;
+    if (perm.levels == 0) {
+      if (total < 0x7fffffffll) {
+        n = (int)((unsigned)row / (unsigned)rows);
+        r = (int)((unsigned)row - (unsigned)n * (unsigned)rows);
       } else {
-        // tap-major order (row < 2^31): peel one tap digit per block, outermost first; digit i has
-        // weight w_1 * ... * w_(i-1) in the frame index, the in-sample row of the last block the
-        // product of all widths
-        unsigned j = (unsigned)row;
-        int frame = 0, weight = 1;
-        for (int lv = 0; lv < perm.levels; ++lv) {
-          const unsigned dgt = j / perm.region[lv];
-          j -= dgt * perm.region[lv];
-          frame += (int)dgt * weight;
-          weight *= perm.width[lv];
-        }
-        n = j / (unsigned)perm.last_rows;
-        r = frame + (long long)(j - (unsigned)n * (unsigned)perm.last_rows) * weight;
+        r = (int)(row % rows);
+        n = (int)(row / rows);
       }
-      s_src[rl] = (n * T + r * frame_step) * c_raw;
+    } else {
+      // tap-major order (row < 2^31): peel one tap digit per block, outermost first; digit i has
+      // weight w_1 * ... * w_(i-1) in the frame index, the in-sample row of the last block the
+      // product of all widths
+      unsigned j = (unsigned)row;
+      int frame = 0, weight = 1;
+      for (int lv = 0; lv < perm.levels; ++lv) {
+        const unsigned dgt = j / perm.region[lv];
+        j -= dgt * perm.region[lv];
+        frame += (int)dgt * weight;
+        weight *= perm.width[lv];
+      }
+      n = (int)(j / (unsigned)perm.last_rows);
+      r = frame + (int)(j - (unsigned)n * (unsigned)perm.last_rows) * weight;
     }
-    __syncthreads();
-    if (live) {
-      const float* src = x + s_src[rl];
-      __align__(16) __nv_bfloat16 hi[8];
-      __align__(16) __nv_bfloat16 lo[8];
+    const float* src = x + ((long long)n * T + (long long)r * frame_step) * c_raw;
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = g * 8 + j;
-        const float v = (k < k_valid) ? __ldg(src + k) : 0.0f;
-        if (f16) hi[j] = f16_bits(v); else split_bf16(v, hi[j], lo[j]);
-      }
-      __nv_bfloat16* dst = out + row * k_pad + g * 8;
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-      if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(lo);
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      const float v = (k < k_valid) ? __ldg(src + k) : 0.0f;
+      if (f16) hi[j] = f16_bits(v); else split_bf16(v, hi[j], lo[j]);
     }
-    __syncthreads();
+    __nv_bfloat16* dst = out + row * k_pad + g * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -86,14 +87,13 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   PackPerm pp;
   memset(&pp, 0, sizeof(pp));
   if (perm) pp = *perm;
-  const long long total_rows = (long long)N * rows;
-  if (total_rows <= 0) return cudaSuccess;
-  if (k_pad % 8 || k_pad > 2048) return cudaErrorInvalidValue;
-  const int rows_per_block = 256 / (k_pad >> 3);
-  long long blocks = (total_rows + rows_per_block - 1) / rows_per_block;
+  const long long total = (long long)N * rows * (k_pad >> 3);
+  if (total <= 0) return cudaSuccess;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_input_kernel<<<(int)blocks, 256, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
-                                                     frame_step, k_pad, plane_stride, pp, f16);
+  pack_input_kernel<<<(int)blocks, threads, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
+                                                         frame_step, k_pad, plane_stride, pp, f16);
   return cudaGetLastError();
 }
 
