@@ -19,7 +19,16 @@ $(LIBDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker --exclude-libs=ALL
 
+# Debug build with in-kernel time stamps (tools/timeline.py): a second library next to the product one.
+DBGDIR    := $(LIBDIR)/dbg
+DBGOBJS   := $(SRCS:$(CSRC)/%.cu=$(DBGDIR)/%.o)
+$(DBGDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(DBGDIR)
+	$(NVCC) $(NVFLAGS) -DVP3D_TIMELINE -c $< -o $@
+dbg: $(DBGOBJS)
+	$(NVCC) $(ARCH) -shared -o $(DBGDIR)/libvp3d_b200.so $(DBGOBJS) -Xlinker --exclude-libs=ALL
+
 clean:
 	rm -rf $(LIBDIR)
 
-.PHONY: all clean
+.PHONY: all clean dbg

@@ -24,6 +24,9 @@ VP3D_SEMI_POS, VP3D_SEMI_TRAJ, VP3D_SEMI_PROJ, VP3D_SEMI_BONE = 1, 2, 4, 8
 
 _LIB_NAME = "libvp3d_b200.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", _LIB_NAME)
+# development hook: another build of the same library (the time-stamping `make dbg` build that
+# tools/timeline.py drives); never a different implementation
+_LIB_PATH = os.environ.get("VP3D_LIB_PATH", _LIB_PATH)
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 STAGE_FN = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)

@@ -124,6 +124,49 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[7] += bf16_hi_to_f(u.w);
 }
 
+// 32 accumulator columns -> affine -> 16-bit pairs -> ReLU on the pairs (lean inference epilogue).
+// All affine loads are issued before the math so that their latency is paid once per chunk.
+template <bool F16>
+__device__ __forceinline__ void lean_chunk(const float* v, const float* s_scale,
+                                           const float* s_shift, uint32_t* hi) {
+  float4 sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = *reinterpret_cast<const float4*>(s_scale + 4 * j);
+    sh[j] = *reinterpret_cast<const float4*>(s_shift + 4 * j);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float r0, r1, r2, r3;
+    ffma2(r0, r1, v[4 * j + 0], v[4 * j + 1], sc[j].x, sc[j].y, sh[j].x, sh[j].y);
+    ffma2(r2, r3, v[4 * j + 2], v[4 * j + 3], sc[j].z, sc[j].w, sh[j].z, sh[j].w);
+    if (F16) {
+      hi[2 * j] = relu_f16x2(pack_f16x2(r0, r1));
+      hi[2 * j + 1] = relu_f16x2(pack_f16x2(r2, r3));
+    } else {
+      hi[2 * j] = relu_bf16x2(pack_bf16x2(r0, r1));
+      hi[2 * j + 1] = relu_bf16x2(pack_bf16x2(r2, r3));
+    }
+  }
+}
+
+#ifdef VP3D_TIMELINE
+__device__ __forceinline__ void tl_stamp(const ConvGemmArgs& p, int ev) {
+  if (!p.timeline) return;
+  int slot;
+  if (blockIdx.x == 0) slot = 0;
+  else if (blockIdx.x == gridDim.x - 1) slot = 1;
+  else return;
+  unsigned long long g;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+  p.timeline[(slot * 16 + ev) * 2] = g;
+  p.timeline[(slot * 16 + ev) * 2 + 1] = (unsigned long long)clock64();
+}
+#define TL(ev) tl_stamp(p, ev)
+#else
+#define TL(ev) ((void)0)
+#endif
+
 // TRAIN compiles in the training-only epilogue paths (BatchNorm batch statistics of the stored
 // value, fused BatchNorm-backward reductions); eval launches use the leaner TRAIN = false build.
 template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
@@ -162,6 +205,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL(0);
 
   const int m_tiles = p.dilated ? p.samples * p.tiles_per_sample : p.tiles_per_sample;
   // Work distribution.  A "worker" is a CTA, or a CTA pair; work item w covers N block w % n_tiles of
@@ -219,11 +263,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TL(1);
   // Everything above touched only this CTA's shared memory / TMEM.  From here on global memory
   // written by the previous kernel of the stream is read: wait for it (no-op without PDL), then let
   // the next kernel start its own prologue on SMs this grid leaves.
   griddep_wait();
   griddep_launch_dependents();
+  if (threadIdx.x == 0) TL(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -258,10 +304,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (PAIR) {
                 // both CTAs' tiles are credited to the leader's barrier (the MMA issuer waits there)
                 const uint32_t lbar = leader_cta_addr(full_bar + stage * 8);
+#ifdef VP3D_TIMELINE
+                const bool skip_w = (p.exp & 1) && (kb & 1), skip_a = (p.exp & 2) && (kb & 1);
+                if (is_leader)
+                  mbar_expect_tx(full_bar + stage * 8, 2 * ((skip_a ? 0u : Cfg::kABytes) +
+                                                            (skip_w ? 0u : Cfg::kBBytes)));
+                if (!skip_a)
+                  tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes,
+                                   a_col0 + kb * kBlockK, a_row, sample, a_plane);
+                if (!skip_w)
+                  tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
+#else
                 if (is_leader) mbar_expect_tx(full_bar + stage * 8, 2 * Cfg::kStageBytes);
                 tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes,
                                  a_col0 + kb * kBlockK, a_row, sample, a_plane);
                 tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
+#endif
               } else {
                 mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
                 tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
@@ -271,6 +329,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                               kb * kBlockK, w_row);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
+#ifdef VP3D_TIMELINE
+              if (w == worker && pair == 0 && tap == 0 && kb == 0) TL(3);
+#endif
             }
           }
         }
@@ -293,6 +354,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(full_bar + stage * 8, phase);
           tc_fence_after();
+#ifdef VP3D_TIMELINE
+          if (w == worker && it == 0) TL(4);
+#endif
           const uint64_t desc_a = make_smem_desc_k_sw128(smem_a + stage * Cfg::kABytes);
           // resident slab index: pairs 0 and 1 read the hi plane of W, pair 2 the lo plane
           const int wi = WRES ? ((it / per_pair == 2 ? per_pair : 0) + it % per_pair) : 0;
@@ -313,6 +377,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (PAIR) umma_commit_pair(tfull_bar + acc * 8);
         else umma_commit(tfull_bar + acc * 8);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef VP3D_TIMELINE
+        if (w == worker) TL(5);
+        TL(6);
+#endif
       }
     }
   } else if (warp == 3) {
@@ -356,6 +424,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
     const bool two_planes = OUT2 && p.out_planes == 2;
+    // (kernel-uniform part of the lean-path condition, see the chunk loop)
+    const bool lean_ok = do_affine && do_relu && !do_f32 && !two_planes;
     // swizzled tile address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
     const uint32_t stage_row = r_in_tile * 128;
     const uint32_t sw = r_in_tile & 7;
@@ -420,6 +490,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // release must not run ahead of the MMAs that refill this TMEM stage.
       mbar_wait(tfull_bar + acc * 8, acc_phase);
       tc_fence_after();
+#ifdef VP3D_TIMELINE
+      if (warp == 4 && lane == 0) { if (w == worker) TL(7); TL(8); }
+#endif
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
       if (last_owned < 0) {
         tc_fence_before();
@@ -491,7 +564,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-          if (do_affine) {
+          // Lean path of the plain inference layers (affine + ReLU, one 16-bit plane, no residual):
+          // paired FMAs, and the ReLU applied to the packed pairs -- 48 instead of 80 math
+          // instructions per 32 columns in a loop that is bound by instruction issue.
+          uint32_t hi[16];
+          const bool lean = kPreload && lean_ok && !res_here;
+          if (lean) {
+            const int cl = c0 - n_blk * BLOCK_N;
+            if (f16) lean_chunk<true>(v, s_scale + cl, s_shift + cl, hi);
+            else lean_chunk<false>(v, s_scale + cl, s_shift + cl, hi);
+          }
+
+          if (!lean && do_affine) {
             const int cl = c0 - n_blk * BLOCK_N;   // column inside the N block
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -503,7 +587,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
             }
           }
-          if (do_relu) {
+          if (!lean && do_relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
@@ -542,8 +626,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (c0 + j < p.n_valid) op[j] = v[j];
             }
           } else {
-            uint32_t hi[16];
-            if (f16) {
+            if (lean) {
+              // already packed
+            } else if (f16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) hi[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
             } else {
@@ -690,9 +775,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef VP3D_TIMELINE
+      if (warp == 4 && lane == 0) { if (w == worker) TL(9); TL(10); }
+#endif
     }
     // the staging tiles must outlive every bulk store that reads them
     if (lane == 0) tma_store_wait_all<0>();
+#ifdef VP3D_TIMELINE
+    if (warp == 4 && lane == 0) TL(11);
+#endif
   }
 
   __syncwarp();
@@ -700,6 +791,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // pairs: neither CTA may leave (or free TMEM) while the other can still read its shared memory
   // through the pair MMAs or signal its barriers
   if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) TL(12);
   if (warp == 2) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
@@ -822,10 +914,31 @@ bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms) {
   return m_tiles >= 2;
 }
 
+#ifdef VP3D_TIMELINE
+static unsigned long long* g_timeline = nullptr;
+static int g_timeline_max = 0, g_timeline_next = 0;
+void conv_gemm_debug_set_timeline(unsigned long long* buf, int max_launches) {
+  g_timeline = buf;
+  g_timeline_max = max_launches;
+  g_timeline_next = 0;
+}
+#endif
+
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,
+                             const CUtensorMap& tmap_z, const ConvGemmArgs& args_in, int block_n,
                              int num_sms, cudaStream_t stream) {
+#ifdef VP3D_TIMELINE
+  ConvGemmArgs args = args_in;
+  args.timeline = (g_timeline && g_timeline_next < g_timeline_max)
+                      ? g_timeline + (size_t)(g_timeline_next++) * 64 : nullptr;
+  {
+    const char* e = getenv("VP3D_EXP");
+    args.exp = e ? atoi(e) : 0;
+  }
+#else
+  const ConvGemmArgs& args = args_in;
+#endif
   const bool res = args.res_tma != 0 || args.bnb != 0;
   const bool wres = conv_gemm_uses_wres(args, block_n, num_sms);
   switch (block_n) {

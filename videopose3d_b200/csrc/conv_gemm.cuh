@@ -97,7 +97,16 @@ struct ConvGemmArgs {
   // two output planes: the lo plane is only produced for tiles that intersect rows
   // [lo_row_begin, lo_row_end) (flat tiling; the rows a later residual add / split-bf16 GEMM reads)
   int lo_row_begin, lo_row_end;
+#ifdef VP3D_TIMELINE
+  // debug build (`make dbg`): per-launch time stamps of the first and the last CTA, and traffic
+  // experiments (exp bit 0 / 1: skip the W / A loads of odd k-blocks -- wrong results, timing only)
+  unsigned long long* timeline;   // [2 CTAs][16 events][globaltimer ns, clock64] or null
+  int exp;
+#endif
 };
+#ifdef VP3D_TIMELINE
+void conv_gemm_debug_set_timeline(unsigned long long* buf, int max_launches);
+#endif
 
 // Host-side launcher (conv_gemm.cu). tmap_a: 4-D (k, row, sample, plane); tmap_w: 2-D (k, slab row);
 // tmap_out: 4-D (channel, row, sample, plane) over the bf16 output, box (64, 32, 1, 1) (ignored —

@@ -20,63 +20,82 @@ __device__ __forceinline__ __nv_bfloat16 f16_bits(float v) {
   return __ushort_as_bfloat16(h);
 }
 
-// One thread per (row, 8-column group): 16-byte stores, coalesced along the row.
-__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                  int planes, int N, int T, int c_raw, int rows, int group,
-                                  int frame_step, int k_pad, long long plane_stride,
-                                  const PackPerm perm, int f16) {
-  const int groups_per_row = k_pad >> 3;
-  const long long total = (long long)N * rows * groups_per_row;
+// Rows are walked in SOURCE order (sample, then frame group): consecutive warps read consecutive
+// bytes of x, which is what DRAM wants -- in the tap-major row order neighbouring output rows come
+// from different samples (33 KB apart for 243-frame windows), and walking the output order
+// turned the read into scattered 400-byte pieces (1.6 TB/s).  The scattered side is the 16-bit
+// output instead, which stays in L2 for the expand GEMM.
+// A row is handled by k_pad/8 neighbouring lanes; lane g converts the element pairs g + G*q
+// (q = 0..3, G = k_pad/8): 8-byte loads and 4-byte stores, both contiguous across the lanes.
+template <bool VEC2>
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int planes, int N,
+                  int T, int c_raw, int rows, int group, int frame_step, int k_pad,
+                  long long plane_stride, const PackPerm perm, int f16) {
+  const int G = k_pad >> 3;                       // lanes per row
+  const long long total = (long long)N * rows * G;
   const int k_valid = group * c_raw;
+  const bool small = total < 0x7fffffffll;        // 32-bit index math (the common case)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int g;
-    long long row;
-    if (total < 0x7fffffffll) {  // 32-bit index math (the common case): far cheaper divisions
+    int g, r;
+    long long n;
+    if (small) {
       const unsigned iu = (unsigned)i;
-      const unsigned ru = iu / (unsigned)groups_per_row;
-      g = (int)(iu - ru * (unsigned)groups_per_row);
-      row = ru;
+      const unsigned sr = iu / (unsigned)G;       // source row = n * rows + r
+      g = (int)(iu - sr * (unsigned)G);
+      const unsigned nu = sr / (unsigned)rows;
+      r = (int)(sr - nu * (unsigned)rows);
+      n = nu;
     } else {
-      g = (int)(i % groups_per_row);
-      row = i / groups_per_row;
+      const long long sr = i / G;
+      g = (int)(i - sr * G);
+      n = sr / rows;
+      r = (int)(sr - n * rows);
     }
-    int r, n;
+    // output row: natural order n*rows + r, or the tap-major position (pack.cuh): peel one tap
+    // digit per block, innermost frame digit first
+    long long row;
     if (perm.levels == 0) {
-      if (total < 0x7fffffffll) {
-        n = (int)((unsigned)row / (unsigned)rows);
-        r = (int)((unsigned)row - (unsigned)n * (unsigned)rows);
-      } else {
-        r = (int)(row % rows);
-        n = (int)(row / rows);
-      }
+      row = n * rows + r;
     } else {
-      // tap-major order (row < 2^31): peel one tap digit per block, outermost first; digit i has
-      // weight w_1 * ... * w_(i-1) in the frame index, the in-sample row of the last block the
-      // product of all widths
-      unsigned j = (unsigned)row;
-      int frame = 0, weight = 1;
+      unsigned t = (unsigned)r;
+      row = 0;
       for (int lv = 0; lv < perm.levels; ++lv) {
-        const unsigned dgt = j / perm.region[lv];
-        j -= dgt * perm.region[lv];
-        frame += (int)dgt * weight;
-        weight *= perm.width[lv];
+        const unsigned w = (unsigned)perm.width[lv];
+        const unsigned q = t / w;
+        row += (long long)(t - q * w) * perm.region[lv];
+        t = q;
       }
-      n = (int)(j / (unsigned)perm.last_rows);
-      r = frame + (int)(j - (unsigned)n * (unsigned)perm.last_rows) * weight;
+      row += n * perm.last_rows + t;
     }
-    const float* src = x + ((long long)n * T + (long long)r * frame_step) * c_raw;
-    __align__(16) __nv_bfloat16 hi[8];
-    __align__(16) __nv_bfloat16 lo[8];
+    const float* src = x + (n * T + (long long)r * frame_step) * c_raw;
+    __nv_bfloat16* dst = out + row * k_pad;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      const float v = (k < k_valid) ? __ldg(src + k) : 0.0f;
-      if (f16) hi[j] = f16_bits(v); else split_bf16(v, hi[j], lo[j]);
+    for (int q = 0; q < 4; ++q) {
+      const int k = 2 * (g + G * q);
+      float v0 = 0.0f, v1 = 0.0f;
+      if (VEC2) {   // c_raw even and x 8-byte aligned: k_valid is even too
+        if (k < k_valid) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(src + k));
+          v0 = v.x;
+          v1 = v.y;
+        }
+      } else {
+        if (k < k_valid) v0 = __ldg(src + k);
+        if (k + 1 < k_valid) v1 = __ldg(src + k + 1);
+      }
+      __nv_bfloat162 hi, lo;
+      if (f16) {
+        hi.x = f16_bits(v0);
+        hi.y = f16_bits(v1);
+      } else {
+        split_bf16(v0, hi.x, lo.x);
+        split_bf16(v1, hi.y, lo.y);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(dst + k) = hi;
+      if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(dst + plane_stride + k) = lo;
     }
-    __nv_bfloat16* dst = out + row * k_pad + g * 8;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-    if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -87,13 +106,19 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   PackPerm pp;
   memset(&pp, 0, sizeof(pp));
   if (perm) pp = *perm;
+  if (k_pad % 8) return cudaErrorInvalidValue;
   const long long total = (long long)N * rows * (k_pad >> 3);
   if (total <= 0) return cudaSuccess;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_input_kernel<<<(int)blocks, threads, 0, stream>>>(x, out, planes, N, T, c_raw, rows, group,
-                                                         frame_step, k_pad, plane_stride, pp, f16);
+  const bool vec2 = (c_raw % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
+  if (vec2)
+    pack_input_kernel<true><<<(int)blocks, threads, 0, stream>>>(
+        x, out, planes, N, T, c_raw, rows, group, frame_step, k_pad, plane_stride, pp, f16);
+  else
+    pack_input_kernel<false><<<(int)blocks, threads, 0, stream>>>(
+        x, out, planes, N, T, c_raw, rows, group, frame_step, k_pad, plane_stride, pp, f16);
   return cudaGetLastError();
 }
 

@@ -304,6 +304,30 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// Two fp32 FMAs in one instruction (FFMA2, sm_100): (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1), each
+// lane rounded exactly like fmaf.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1,
+                                      float c0, float c1) {
+  unsigned long long a, b, c, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// ReLU on a packed pair (max with +0 commutes with the rounding that produced the pair)
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t v) {
+  uint32_t r;
+  const uint32_t z = 0u;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(z));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t r;
+  const uint32_t z = 0u;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(z));
+  return r;
+}
 __device__ __forceinline__ float f16_lo_to_f(uint32_t v) {
   return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu)));
 }
