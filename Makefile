@@ -28,7 +28,11 @@ $(DBGDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 dbg: $(DBGOBJS)
 	$(NVCC) $(ARCH) -shared -o $(DBGDIR)/libvp3d_b200.so $(DBGOBJS) -Xlinker --exclude-libs=ALL
 
+micro: tools/micro/pack_bench.cu $(CSRC)/pack.cu $(HDRS)
+	@mkdir -p $(DBGDIR)
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo tools/micro/pack_bench.cu $(CSRC)/pack.cu -o $(DBGDIR)/pack_bench
+
 clean:
 	rm -rf $(LIBDIR)
 
-.PHONY: all clean dbg
+.PHONY: all clean dbg micro

@@ -34,10 +34,14 @@ g = torch.Generator().manual_seed(0)
 x = (torch.rand(N, T, J, F, generator=g) * 2 - 1).to(dev)
 m = vp.TemporalModel(J, F, J, filter_widths=ARC, channels=C).to(dev).eval().set_precision(prec)
 L = 32
-buf = torch.zeros(L, 2, 16, 2, dtype=torch.int64, device=dev)
+buf = torch.zeros(L, 2, 32, 2, dtype=torch.int64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 EV = ["entry", "setup", "depwait", "tma0", "land0", "mma_t0", "mma_tN", "epi_t0", "epi_tN_in",
-      "epi_t0_out", "epi_tN_out", "drained", "exit"]
+      "epi_t0_out", "epi_tN_out", "drained", "exit",
+      # first tile, first / second store block of epilogue warp 4: accumulator in registers, first /
+      # second half staged, TMA store issued
+      "b0_ld", "b0_h0", "b0_h1", "b0_st", "b1_ld", "b1_h0", "b1_h1", "b1_st"]
+NE = len(EV)
 with torch.no_grad():
     for _ in range(3):
         m(x)
@@ -64,8 +68,8 @@ with torch.no_grad():
             for cta in (0, 1):
                 if t[li, cta, 0, 0] == 0:
                     continue
-                gt = t[li, cta, :13, 0].astype("int64")
-                ck = t[li, cta, :13, 1].astype("int64")
+                gt = t[li, cta, :NE, 0].astype("int64")
+                ck = t[li, cta, :NE, 1].astype("int64")
                 rel = [(int(v) - t0) / 1e3 if v else float("nan") for v in gt]
                 cyc = [(int(v) - int(ck[0])) if v else -1 for v in ck]
                 print(f"L{li:02d} cta{'0' if cta == 0 else 'N'} us: " +

@@ -329,7 +329,7 @@ extern "C" __attribute__((visibility("default"))) int vp3d_set_sm_limit(int n) {
 }
 extern "C" __attribute__((visibility("default"))) const char* vp3d_last_error(void) { return g_err; }
 #ifdef VP3D_TIMELINE
-// debug build only (`make dbg`, tools/timeline.py): device buffer of [max_launches][2][16][2] u64
+// debug build only (`make dbg`, tools/timeline.py): device buffer of [max_launches][2][32][2] u64
 extern "C" __attribute__((visibility("default"))) int vp3d_debug_set_timeline(unsigned long long* buf,
                                                                                 int max_launches) {
   vp3d::conv_gemm_debug_set_timeline(buf, max_launches);

@@ -37,9 +37,15 @@ namespace vp3d {
 // multiple of the number of N blocks so that a CTA keeps its N block for all of its tiles.
 // OUT2: two output planes (hi, lo) -> each epilogue group needs two staging tiles; the extra 32 KiB
 // come out of the operand pipeline.
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool PAIR = false>
+// LEAN (inference layers: affine + ReLU [+ one-plane TMA residual] -> one 16-bit plane): a dedicated
+// epilogue with every option resolved at compile time.  With a residual it works IN PLACE: the
+// result overwrites the residual tile it has just consumed and the bulk store reads from there, so
+// no staging tiles are needed and the operand pipeline gets their 32 KiB (5 instead of 4 stages
+// on CTA pairs).
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool PAIR = false, bool LEAN = false>
 struct GemmCfg {
   static_assert(!(RES && WRES), "W-resident variant has no residual path");
+  static_assert(!(LEAN && OUT2), "the lean epilogue writes one plane");
   static_assert(!PAIR || (BLOCK_N == 256 && !WRES), "CTA pairs run 256-wide, streamed-W tiles");
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
@@ -47,14 +53,16 @@ struct GemmCfg {
   static constexpr uint32_t kWResBytes = WRES ? 128u * 1024u : 0u;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages
   static constexpr uint32_t kTileBytes = kBlockM * 64 * 2;  // one 128 x 64 bf16 tile (16 KiB)
-  static constexpr int kStoreTiles = OUT2 ? 4 : 2;          // one (hi[, lo]) set per epilogue group
+  // one (hi[, lo]) set per epilogue group; none when the result is staged in the residual tile
+  static constexpr int kStoreTiles = (LEAN && RES) ? 0 : (OUT2 ? 4 : 2);
   // auxiliary (residual / Z) landing tiles: 3 next to 128x256 tiles, 4 next to narrower ones, so
   // that two-tile store blocks (hi+lo residual, or residual + Z) still get two stages in flight
   // (with two output planes the four staging tiles already take 64 KiB: one auxiliary stage only,
   // the second epilogue group covers the exposed load latency, and the operand pipeline keeps its
   // depth)
   // (CTA pairs stream half the W bytes per stage: a fourth landing tile fits next to 4 stages)
-  static constexpr int kResSlots = RES ? ((BLOCK_N == 256 && !PAIR) ? 3 : 4) : 0;
+  // (in place: a slot stays busy until its store has drained -- four slots, two per group)
+  static constexpr int kResSlots = RES ? ((BLOCK_N == 256 && !PAIR && !LEAN) ? 3 : 4) : 0;
   static constexpr uint32_t kFixedBytes = kWResBytes + (kStoreTiles + kResSlots) * kTileBytes;
   // per-channel affine (scale, shift) of the current N block: 2 x BLOCK_N floats
   static constexpr uint32_t kAffineBytes = 2 * BLOCK_N * 4;
@@ -124,10 +132,11 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[7] += bf16_hi_to_f(u.w);
 }
 
-// 32 accumulator columns -> affine -> 16-bit pairs -> ReLU on the pairs (lean inference epilogue).
-// All affine loads are issued before the math so that their latency is paid once per chunk.
+// Lean inference epilogue, 32 accumulator columns of one row:
+//   plain:    affine (paired FMAs) -> 16-bit pairs -> ReLU on the pairs
+//   residual: affine -> ReLU -> + residual (32 16-bit values in rres[0..3]) -> 16-bit pairs
 template <bool F16>
-__device__ __forceinline__ void lean_chunk(const float* v, const float* s_scale,
+__device__ __forceinline__ void lean_chunk(const uint32_t* a, const float* s_scale,
                                            const float* s_shift, uint32_t* hi) {
   float4 sc[8], sh[8];
 #pragma unroll
@@ -138,14 +147,49 @@ __device__ __forceinline__ void lean_chunk(const float* v, const float* s_scale,
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float r0, r1, r2, r3;
-    ffma2(r0, r1, v[4 * j + 0], v[4 * j + 1], sc[j].x, sc[j].y, sh[j].x, sh[j].y);
-    ffma2(r2, r3, v[4 * j + 2], v[4 * j + 3], sc[j].z, sc[j].w, sh[j].z, sh[j].w);
+    ffma2(r0, r1, __uint_as_float(a[4 * j + 0]), __uint_as_float(a[4 * j + 1]), sc[j].x, sc[j].y,
+          sh[j].x, sh[j].y);
+    ffma2(r2, r3, __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3]), sc[j].z, sc[j].w,
+          sh[j].z, sh[j].w);
     if (F16) {
       hi[2 * j] = relu_f16x2(pack_f16x2(r0, r1));
       hi[2 * j + 1] = relu_f16x2(pack_f16x2(r2, r3));
     } else {
       hi[2 * j] = relu_bf16x2(pack_bf16x2(r0, r1));
       hi[2 * j + 1] = relu_bf16x2(pack_bf16x2(r2, r3));
+    }
+  }
+}
+
+template <bool F16>
+__device__ __forceinline__ void lean_chunk_res(const uint32_t* a, const float* s_scale,
+                                               const float* s_shift, const uint4* rres,
+                                               uint32_t* hi) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + 4 * j);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + 4 * j);
+    float r0, r1, r2, r3;
+    ffma2(r0, r1, __uint_as_float(a[4 * j + 0]), __uint_as_float(a[4 * j + 1]), sc.x, sc.y, sh.x,
+          sh.y);
+    ffma2(r2, r3, __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3]), sc.z, sc.w, sh.z,
+          sh.w);
+    const uint4 u4 = rres[j >> 1];
+    const uint32_t u0 = (j & 1) ? u4.z : u4.x, u1 = (j & 1) ? u4.w : u4.y;
+    if (F16) {
+      r0 = fmaxf(r0, 0.0f) + f16_lo_to_f(u0);
+      r1 = fmaxf(r1, 0.0f) + f16_hi_to_f(u0);
+      r2 = fmaxf(r2, 0.0f) + f16_lo_to_f(u1);
+      r3 = fmaxf(r3, 0.0f) + f16_hi_to_f(u1);
+      hi[2 * j] = pack_f16x2(r0, r1);
+      hi[2 * j + 1] = pack_f16x2(r2, r3);
+    } else {
+      r0 = fmaxf(r0, 0.0f) + bf16_lo_to_f(u0);
+      r1 = fmaxf(r1, 0.0f) + bf16_hi_to_f(u0);
+      r2 = fmaxf(r2, 0.0f) + bf16_lo_to_f(u1);
+      r3 = fmaxf(r3, 0.0f) + bf16_hi_to_f(u1);
+      hi[2 * j] = pack_bf16x2(r0, r1);
+      hi[2 * j + 1] = pack_bf16x2(r2, r3);
     }
   }
 }
@@ -159,8 +203,8 @@ __device__ __forceinline__ void tl_stamp(const ConvGemmArgs& p, int ev) {
   else return;
   unsigned long long g;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-  p.timeline[(slot * 16 + ev) * 2] = g;
-  p.timeline[(slot * 16 + ev) * 2 + 1] = (unsigned long long)clock64();
+  p.timeline[(slot * 32 + ev) * 2] = g;
+  p.timeline[(slot * 32 + ev) * 2 + 1] = (unsigned long long)clock64();
 }
 #define TL(ev) tl_stamp(p, ev)
 #else
@@ -169,14 +213,15 @@ __device__ __forceinline__ void tl_stamp(const ConvGemmArgs& p, int ev) {
 
 // TRAIN compiles in the training-only epilogue paths (BatchNorm batch statistics of the stored
 // value, fused BatchNorm-backward reductions); eval launches use the leaner TRAIN = false build.
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_z, const ConvGemmArgs p) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR>;
+  static_assert(!LEAN || !TRAIN, "the lean epilogue is inference-only");
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR, LEAN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBlocksPerTile = BLOCK_N / 64;
 
@@ -248,7 +293,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(rfull_bar + s * 8, 1);
-      mbar_init(rempty_bar + s * 8, 128);  // one group consumes an auxiliary stage
+      // one group consumes an auxiliary stage (in place: its four store-issuing lanes hand it back)
+      mbar_init(rempty_bar + s * 8, LEAN ? 4 : 128);
     }
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
@@ -409,6 +455,133 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
+  } else if (warp >= 4 && LEAN) {
+    // ------------------------------------------------------------ lean inference epilogue
+    // Same roles as below (two groups of four warps, alternating 64-column store blocks, per-warp
+    // 32-row bulk stores), with affine + ReLU [+ residual] -> one 16-bit plane fixed at compile
+    // time.  Residual variant: store block b uses landing slot b % 4 -- always the same group's --
+    // and the result is written over the residual bytes this very thread has consumed; the slot
+    // goes back to the auxiliary producer when the four bulk stores issued from it have read it.
+    const int eg = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int r_in_tile = ew * 32 + lane;
+    const uint32_t stage_row = r_in_tile * 128;
+    const uint32_t sw = r_in_tile & 7;
+    const bool f16 = p.f16 != 0;
+    const uint32_t tempty_addr = PAIR ? leader_cta_addr(tempty_bar) : tempty_bar;
+    uint32_t acc = 0, acc_phase = 0;
+    uint32_t gblock = 0;
+    int aff_n_blk = -1;
+    uint32_t held_slot = 0;
+    bool holding = false;
+    for (int w = worker; w < total_tiles; w += num_workers) {
+      int n_blk, sample, row0;
+      tile_coords(p, tile_of(w), n_blk, sample, row0);
+      if (n_blk != aff_n_blk) {   // per-channel affine of this N block -> shared memory
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const int e = (int)threadIdx.x - 128;
+        if (e < BLOCK_N) {
+          s_affine[e] = __ldg(p.scale + n_blk * BLOCK_N + e);
+          s_affine[BLOCK_N + e] = __ldg(p.shift + n_blk * BLOCK_N + e);
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        aff_n_blk = n_blk;
+      }
+      int last_owned = -1;
+#pragma unroll
+      for (int sb = 0; sb < kBlocksPerTile; ++sb)
+        if (((gblock + (uint32_t)sb) & 1u) == (uint32_t)eg) last_owned = sb;
+      mbar_wait(tfull_bar + acc * 8, acc_phase);
+      tc_fence_after();
+#ifdef VP3D_TIMELINE
+      if (warp == 4 && lane == 0) { if (w == worker) TL(7); TL(8); }
+#endif
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
+      if (last_owned < 0) {
+        tc_fence_before();
+        if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+      }
+#pragma unroll 1
+      for (int sb = 0; sb < kBlocksPerTile; ++sb, ++gblock) {
+        if ((gblock & 1u) != (uint32_t)eg) continue;
+        const int cb = n_blk * BLOCK_N + sb * 64;
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(t_addr + sb * 64, a0);
+        tmem_ld_32x32(t_addr + sb * 64 + 32, a1);
+        uint32_t tile_base = smem_store + eg * Cfg::kTileBytes;
+        uint4 rres[RES ? 8 : 1];
+        if (RES) {
+          const uint32_t rs = gblock & 3u;
+          if (holding && lane == 0) {
+            // this group's previous block: its bulk stores have read the slot -> refill allowed
+            tma_store_wait_read<0>();
+            mbar_arrive(rempty_bar + held_slot * 8);
+          }
+          held_slot = rs;
+          holding = true;
+          mbar_wait(rfull_bar + rs * 8, (gblock >> 2) & 1u);   // residual tile has landed
+          tile_base = smem_res + rs * Cfg::kTileBytes;
+#pragma unroll
+          for (int q = 0; q < (RES ? 8 : 1); ++q)
+            rres[q] = ld_shared_v4(tile_base + stage_row + (((uint32_t)q ^ sw) << 4));
+        }
+        tmem_ld_wait();
+#ifdef VP3D_TIMELINE
+        if (warp == 4 && lane == 0 && w == worker) TL(13 + 4 * (sb >> 1));
+#endif
+        if (sb == last_owned) {
+          tc_fence_before();
+          if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
+        }
+        uint32_t h0[16], h1[16];
+        const float* sc = s_affine + sb * 64;
+        const float* sh = s_affine + BLOCK_N + sb * 64;
+        if (RES) {
+          if (f16) {
+            lean_chunk_res<true>(a0, sc, sh, rres, h0);
+            lean_chunk_res<true>(a1, sc + 32, sh + 32, rres + (RES ? 4 : 0), h1);
+          } else {
+            lean_chunk_res<false>(a0, sc, sh, rres, h0);
+            lean_chunk_res<false>(a1, sc + 32, sh + 32, rres + (RES ? 4 : 0), h1);
+          }
+        } else {
+          if (f16) {
+            lean_chunk<true>(a0, sc, sh, h0);
+            lean_chunk<true>(a1, sc + 32, sh + 32, h1);
+          } else {
+            lean_chunk<false>(a0, sc, sh, h0);
+            lean_chunk<false>(a1, sc + 32, sh + 32, h1);
+          }
+          // the staging slice of this warp must have been read by its previous bulk store
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          st_shared_v4(tile_base + stage_row + (((uint32_t)q ^ sw) << 4), h0[4 * q], h0[4 * q + 1],
+                       h0[4 * q + 2], h0[4 * q + 3]);
+          st_shared_v4(tile_base + stage_row + (((uint32_t)(4 + q) ^ sw) << 4), h1[4 * q],
+                       h1[4 * q + 1], h1[4 * q + 2], h1[4 * q + 3]);
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmap_out, tile_base + (uint32_t)ew * 32u * 128u, cb, row0 + ew * 32, sample, 0);
+          tma_store_commit();
+#ifdef VP3D_TIMELINE
+          if (warp == 4 && w == worker) TL(16 + 4 * (sb >> 1));
+#endif
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef VP3D_TIMELINE
+      if (warp == 4 && lane == 0) { if (w == worker) TL(9); TL(10); }
+#endif
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+#ifdef VP3D_TIMELINE
+    if (warp == 4 && lane == 0) TL(11);
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (two groups)
     const int eg = (warp - 4) >> 2;   // epilogue group 0 / 1
@@ -424,8 +597,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool do_f32 = p.flags & kEpiOutF32;
     const bool do_affine = p.flags & kEpiAffine;
     const bool two_planes = OUT2 && p.out_planes == 2;
-    // (kernel-uniform part of the lean-path condition, see the chunk loop)
-    const bool lean_ok = do_affine && do_relu && !do_f32 && !two_planes;
     // swizzled tile address of this thread's row: chunk j (16 B) lives at j ^ (row & 7)
     const uint32_t stage_row = r_in_tile * 128;
     const uint32_t sw = r_in_tile & 7;
@@ -519,6 +690,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_32x32(t_addr + (sb * 2) * 32, pre[0]);
           tmem_ld_32x32(t_addr + (sb * 2 + 1) * 32, pre[kPreload ? 1 : 0]);
           tmem_ld_wait();
+#ifdef VP3D_TIMELINE
+          if (warp == 4 && lane == 0 && w == worker) TL(13 + 4 * (sb >> 1));
+#endif
           if (sb == last_owned) {
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
@@ -564,18 +738,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-          // Lean path of the plain inference layers (affine + ReLU, one 16-bit plane, no residual):
-          // paired FMAs, and the ReLU applied to the packed pairs -- 48 instead of 80 math
-          // instructions per 32 columns in a loop that is bound by instruction issue.
-          uint32_t hi[16];
-          const bool lean = kPreload && lean_ok && !res_here;
-          if (lean) {
-            const int cl = c0 - n_blk * BLOCK_N;
-            if (f16) lean_chunk<true>(v, s_scale + cl, s_shift + cl, hi);
-            else lean_chunk<false>(v, s_scale + cl, s_shift + cl, hi);
-          }
-
-          if (!lean && do_affine) {
+          if (do_affine) {
             const int cl = c0 - n_blk * BLOCK_N;   // column inside the N block
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -587,7 +750,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
             }
           }
-          if (!lean && do_relu) {
+          if (do_relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
@@ -626,9 +789,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (c0 + j < p.n_valid) op[j] = v[j];
             }
           } else {
-            if (lean) {
-              // already packed
-            } else if (f16) {
+            uint32_t hi[16];
+            if (f16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) hi[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
             } else {
@@ -662,6 +824,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 st_shared_v4(dst_lo + (((half * 4 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1],
                              lo[4 * q + 2], lo[4 * q + 3]);
             }
+#ifdef VP3D_TIMELINE
+            if (kPreload && warp == 4 && lane == 0 && w == worker) TL(14 + half + 4 * (sb >> 1));
+#endif
             if (half == 1) {
               fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
               __syncwarp();
@@ -673,6 +838,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (two_planes_t)
                   tma_store_4d(&tmap_out, src + Cfg::kTileBytes, cb, row0 + ew * 32, sample, 1);
                 tma_store_commit();
+#ifdef VP3D_TIMELINE
+                if (kPreload && warp == 4 && w == worker) TL(16 + 4 * (sb >> 1));
+#endif
               }
             }
           }
@@ -825,13 +993,13 @@ static bool pair_enabled() {
 
 bool conv_gemm_pairs_enabled() { return pair_enabled(); }
 
-template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR>
+template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool TRAIN, bool PAIR, bool LEAN = false>
 static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                                const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                                const CUtensorMap& tmap_z, const ConvGemmArgs& args, int num_sms,
                                cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN, PAIR>;
+  using Cfg = GemmCfg<BLOCK_N, RES, WRES, OUT2, PAIR, LEAN>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, RES, WRES, OUT2, TRAIN, PAIR, LEAN>;
   // the dynamic shared memory opt-in is a per-device attribute
   static bool attr_set[kMaxDevices] = {};
   int dev = 0;
@@ -874,12 +1042,33 @@ static cudaError_t launch_impl(const CUtensorMap& tmap_a, const CUtensorMap& tma
   return cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_w, tmap_out, tmap_res, tmap_z, args);
 }
 
+// Lean inference epilogue (VP3D_LEAN=0 falls back to the general one): exactly affine + ReLU
+// [+ a one-plane TMA residual over every column] into one 16-bit plane.
+static bool lean_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VP3D_LEAN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+static bool lean_ok(const ConvGemmArgs& a, bool res) {
+  if (!lean_enabled() || a.bnb || a.out_planes != 1 || !a.out) return false;
+  if (!res) return a.flags == (kEpiAffine | kEpiRelu) && !a.res_tma;
+  return a.flags == (kEpiAffine | kEpiRelu | kEpiResidual) && a.res_tma && a.res_planes == 1 &&
+         a.res_col_begin == 0 && a.res_cols >= a.n_pad;
+}
+
 template <int BLOCK_N, bool RES, bool WRES, bool OUT2, bool PAIR>
 static cudaError_t launch_train(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
                                 const CUtensorMap& r, const CUtensorMap& z, const ConvGemmArgs& args,
                                 int num_sms, cudaStream_t stream) {
   if ((args.flags & kEpiStats) || args.bnb)
     return launch_impl<BLOCK_N, RES, WRES, OUT2, true, PAIR>(a, w, o, r, z, args, num_sms, stream);
+  if constexpr (!OUT2) {
+    if (lean_ok(args, RES))
+      return launch_impl<BLOCK_N, RES, WRES, false, false, PAIR, true>(a, w, o, r, z, args, num_sms, stream);
+  }
   return launch_impl<BLOCK_N, RES, WRES, OUT2, false, PAIR>(a, w, o, r, z, args, num_sms, stream);
 }
 
@@ -931,7 +1120,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
 #ifdef VP3D_TIMELINE
   ConvGemmArgs args = args_in;
   args.timeline = (g_timeline && g_timeline_next < g_timeline_max)
-                      ? g_timeline + (size_t)(g_timeline_next++) * 64 : nullptr;
+                      ? g_timeline + (size_t)(g_timeline_next++) * 128 : nullptr;
   {
     const char* e = getenv("VP3D_EXP");
     args.exp = e ? atoi(e) : 0;

@@ -100,7 +100,7 @@ struct ConvGemmArgs {
 #ifdef VP3D_TIMELINE
   // debug build (`make dbg`): per-launch time stamps of the first and the last CTA, and traffic
   // experiments (exp bit 0 / 1: skip the W / A loads of odd k-blocks -- wrong results, timing only)
-  unsigned long long* timeline;   // [2 CTAs][16 events][globaltimer ns, clock64] or null
+  unsigned long long* timeline;   // [2 CTAs][32 events][globaltimer ns, clock64] or null
   int exp;
 #endif
 };

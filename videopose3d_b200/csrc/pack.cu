@@ -20,81 +20,106 @@ __device__ __forceinline__ __nv_bfloat16 f16_bits(float v) {
   return __ushort_as_bfloat16(h);
 }
 
-// Rows are walked in SOURCE order (sample, then frame group): consecutive warps read consecutive
-// bytes of x, which is what DRAM wants -- in the tap-major row order neighbouring output rows come
-// from different samples (33 KB apart for 243-frame windows), and walking the output order
-// turned the read into scattered 400-byte pieces (1.6 TB/s).  The scattered side is the 16-bit
-// output instead, which stays in L2 for the expand GEMM.
-// A row is handled by k_pad/8 neighbouring lanes; lane g converts the element pairs g + G*q
-// (q = 0..3, G = k_pad/8): 8-byte loads and 4-byte stores, both contiguous across the lanes.
+// Rows are walked in SOURCE order (sample, then frame group) so that the fp32 read is one
+// sequential stream; the scattered side (tap-major row order) is the 16-bit output, which stays in
+// L2 for the expand GEMM.  A block owns a chunk of at most kPackRows consecutive rows of one sample:
+// the row -> output-row map of the chunk (up to eight integer divisions per row) is computed once
+// into shared memory, then every warp converts whole rows -- lanes stride over the element pairs
+// with 8-byte loads and 4-byte stores, two rows in flight per warp.
+constexpr int kPackRows = 96;
+
+template <bool VEC2>
+__device__ __forceinline__ void pack_load_pair(const float* src, int k, int k_valid, float& v0,
+                                               float& v1) {
+  v0 = 0.0f;
+  v1 = 0.0f;
+  if (VEC2) {   // c_raw even and x 8-byte aligned: k_valid is even too
+    if (k < k_valid) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + k));
+      v0 = v.x;
+      v1 = v.y;
+    }
+  } else {
+    if (k < k_valid) v0 = __ldg(src + k);
+    if (k + 1 < k_valid) v1 = __ldg(src + k + 1);
+  }
+}
+
+__device__ __forceinline__ void pack_store_pair(__nv_bfloat16* dst, long long plane_stride, int planes,
+                                                int f16, float v0, float v1) {
+  __nv_bfloat162 hi, lo;
+  if (f16) {
+    hi.x = f16_bits(v0);
+    hi.y = f16_bits(v1);
+  } else {
+    split_bf16(v0, hi.x, lo.x);
+    split_bf16(v1, hi.y, lo.y);
+  }
+  *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
+  if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(dst + plane_stride) = lo;
+}
+
 template <bool VEC2>
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int planes, int N,
                   int T, int c_raw, int rows, int group, int frame_step, int k_pad,
                   long long plane_stride, const PackPerm perm, int f16) {
-  const int G = k_pad >> 3;                       // lanes per row
-  const long long total = (long long)N * rows * G;
+  __shared__ long long s_row[kPackRows];
+  const int chunks = (rows + kPackRows - 1) / kPackRows;
+  const long long items = (long long)N * chunks;
   const int k_valid = group * c_raw;
-  const bool small = total < 0x7fffffffll;        // 32-bit index math (the common case)
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int g, r;
-    long long n;
-    if (small) {
-      const unsigned iu = (unsigned)i;
-      const unsigned sr = iu / (unsigned)G;       // source row = n * rows + r
-      g = (int)(iu - sr * (unsigned)G);
-      const unsigned nu = sr / (unsigned)rows;
-      r = (int)(sr - nu * (unsigned)rows);
-      n = nu;
-    } else {
-      const long long sr = i / G;
-      g = (int)(i - sr * G);
-      n = sr / rows;
-      r = (int)(sr - n * rows);
-    }
-    // output row: natural order n*rows + r, or the tap-major position (pack.cuh): peel one tap
-    // digit per block, innermost frame digit first
-    long long row;
-    if (perm.levels == 0) {
-      row = n * rows + r;
-    } else {
-      unsigned t = (unsigned)r;
-      row = 0;
-      for (int lv = 0; lv < perm.levels; ++lv) {
-        const unsigned w = (unsigned)perm.width[lv];
-        const unsigned q = t / w;
-        row += (long long)(t - q * w) * perm.region[lv];
-        t = q;
-      }
-      row += n * perm.last_rows + t;
-    }
-    const float* src = x + (n * T + (long long)r * frame_step) * c_raw;
-    __nv_bfloat16* dst = out + row * k_pad;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = 2 * (g + G * q);
-      float v0 = 0.0f, v1 = 0.0f;
-      if (VEC2) {   // c_raw even and x 8-byte aligned: k_valid is even too
-        if (k < k_valid) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(src + k));
-          v0 = v.x;
-          v1 = v.y;
+  const int pairs = k_pad >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long n = item / chunks;
+    const int r0 = (int)(item - n * chunks) * kPackRows;
+    const int nr = min(kPackRows, rows - r0);
+    __syncthreads();   // the previous chunk's map is no longer read
+    if ((int)threadIdx.x < nr) {
+      const int r = r0 + (int)threadIdx.x;
+      // output row: natural order n*rows + r, or the tap-major position (pack.cuh): peel one tap
+      // digit per block, innermost frame digit first
+      long long row;
+      if (perm.levels == 0) {
+        row = n * rows + r;
+      } else {
+        unsigned t = (unsigned)r;
+        row = 0;
+        for (int lv = 0; lv < perm.levels; ++lv) {
+          const unsigned w = (unsigned)perm.width[lv];
+          const unsigned q = t / w;
+          row += (long long)(t - q * w) * perm.region[lv];
+          t = q;
         }
-      } else {
-        if (k < k_valid) v0 = __ldg(src + k);
-        if (k + 1 < k_valid) v1 = __ldg(src + k + 1);
+        row += n * perm.last_rows + t;
       }
-      __nv_bfloat162 hi, lo;
-      if (f16) {
-        hi.x = f16_bits(v0);
-        hi.y = f16_bits(v1);
-      } else {
-        split_bf16(v0, hi.x, lo.x);
-        split_bf16(v1, hi.y, lo.y);
+      s_row[threadIdx.x] = row;
+    }
+    __syncthreads();
+    const float* src0 = x + (n * T + (long long)r0 * frame_step) * c_raw;
+    const long long src_step = (long long)frame_step * c_raw;
+    for (int rl = warp * 2; rl < nr; rl += 16) {   // 8 warps x 2 rows
+      const bool two = rl + 1 < nr;
+      const float* sa = src0 + rl * src_step;
+      const float* sb = sa + src_step;
+      __nv_bfloat16* da = out + s_row[rl] * k_pad;
+      __nv_bfloat16* db = out + s_row[two ? rl + 1 : rl] * k_pad;
+      for (int c = lane; c < pairs; c += 64) {
+        const int c2 = c + 32;
+        float a0, a1, a2, a3, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        pack_load_pair<VEC2>(sa, 2 * c, k_valid, a0, a1);
+        pack_load_pair<VEC2>(sa, 2 * c2, c2 < pairs ? k_valid : 0, a2, a3);
+        if (two) {
+          pack_load_pair<VEC2>(sb, 2 * c, k_valid, b0, b1);
+          pack_load_pair<VEC2>(sb, 2 * c2, c2 < pairs ? k_valid : 0, b2, b3);
+        }
+        pack_store_pair(da + 2 * c, plane_stride, planes, f16, a0, a1);
+        if (c2 < pairs) pack_store_pair(da + 2 * c2, plane_stride, planes, f16, a2, a3);
+        if (two) {
+          pack_store_pair(db + 2 * c, plane_stride, planes, f16, b0, b1);
+          if (c2 < pairs) pack_store_pair(db + 2 * c2, plane_stride, planes, f16, b2, b3);
+        }
       }
-      *reinterpret_cast<__nv_bfloat162*>(dst + k) = hi;
-      if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(dst + plane_stride + k) = lo;
     }
   }
 }
@@ -107,17 +132,16 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   memset(&pp, 0, sizeof(pp));
   if (perm) pp = *perm;
   if (k_pad % 8) return cudaErrorInvalidValue;
-  const long long total = (long long)N * rows * (k_pad >> 3);
-  if (total <= 0) return cudaSuccess;
-  const int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (N <= 0 || rows <= 0) return cudaSuccess;
+  const long long items = (long long)N * ((rows + kPackRows - 1) / kPackRows);
+  long long blocks = items;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   const bool vec2 = (c_raw % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
   if (vec2)
-    pack_input_kernel<true><<<(int)blocks, threads, 0, stream>>>(
+    pack_input_kernel<true><<<(int)blocks, 256, 0, stream>>>(
         x, out, planes, N, T, c_raw, rows, group, frame_step, k_pad, plane_stride, pp, f16);
   else
-    pack_input_kernel<false><<<(int)blocks, threads, 0, stream>>>(
+    pack_input_kernel<false><<<(int)blocks, 256, 0, stream>>>(
         x, out, planes, N, T, c_raw, rows, group, frame_step, k_pad, plane_stride, pp, f16);
   return cudaGetLastError();
 }
