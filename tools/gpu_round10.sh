@@ -21,5 +21,5 @@ for f in ['bench','bench_nolean']:
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file gpurun_out/${TAG}_launches_eval.csv python tools/profile_steps.py eval fp16 > gpurun_out/${TAG}_prof.log 2>&1
 python tools/summarize_launches.py gpurun_out/${TAG}_launches_eval.csv 2>/dev/null | head -14
-timeout 300 python tools/timeline.py fp16 0 > gpurun_out/${TAG}_timeline.txt 2>&1
+timeout 300 python tools/timeline.py fp16 > gpurun_out/${TAG}_timeline.txt 2>&1
 grep "^# rep" gpurun_out/${TAG}_timeline.txt

@@ -7,7 +7,7 @@ set-up done, dependency wait done, first TMA issued, first operands landed, firs
 committed by the MMA issuer, first / last accumulator seen by the epilogue, last store issued,
 stores drained, CTA exit.  Prints one line per launch relative to the first launch's entry.
 
-    python tools/timeline.py [precision] [VP3D_EXP bits]
+    python tools/timeline.py [precision]
 """
 import ctypes
 import os
@@ -16,8 +16,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ.setdefault("VP3D_LIB_PATH",
                       os.path.join(ROOT, "videopose3d_b200", "_lib", "dbg", "libvp3d_b200.so"))
-if len(sys.argv) > 2:
-    os.environ["VP3D_EXP"] = sys.argv[2]
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
@@ -40,7 +38,9 @@ EV = ["entry", "setup", "depwait", "tma0", "land0", "mma_t0", "mma_tN", "epi_t0"
       "epi_t0_out", "epi_tN_out", "drained", "exit",
       # first tile, first / second store block of epilogue warp 4: accumulator in registers, first /
       # second half staged, TMA store issued
-      "b0_ld", "b0_h0", "b0_h1", "b0_st", "b1_ld", "b1_h0", "b1_h1", "b1_st"]
+      "b0_ld", "b0_h0", "b0_h1", "b0_st", "b1_ld", "b1_h0", "b1_h1", "b1_st",
+      # producer thread: its own dependency wait done (after priming the W tiles)
+      "p_wait", "p_primed", "p_w0"]
 NE = len(EV)
 with torch.no_grad():
     for _ in range(3):
@@ -57,7 +57,7 @@ with torch.no_grad():
         torch.cuda.synchronize()
         lib.vp3d_debug_set_timeline(None, 0)
         t = buf.cpu().numpy()
-        print(f"# rep {rep}: forward {e0.elapsed_time(e1) * 1e3:.1f} us (events), EXP={os.environ.get('VP3D_EXP', '0')}")
+        print(f"# rep {rep}: forward {e0.elapsed_time(e1) * 1e3:.1f} us (events) ")
         t0 = None
         prev_exit = None
         for li in range(L):

@@ -245,7 +245,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_slot = wfull_bar + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
-  const uint32_t affine_off = (tmem_slot + 8 - base + 15u) & ~15u;   // [scale | shift][BLOCK_N]
+  const uint32_t dep_bar = tmem_slot + 8;       // "the dependency wait has returned" (see the producer)
+  const uint32_t affine_off = (dep_bar + 8 - base + 15u) & ~15u;   // [scale | shift][BLOCK_N]
   float* s_affine = reinterpret_cast<float*>(smem + affine_off);
 
   const int warp = threadIdx.x >> 5;
@@ -297,6 +298,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(rempty_bar + s * 8, LEAN ? 4 : 128);
     }
     mbar_init(wfull_bar, 1);
+    mbar_init(dep_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -312,15 +314,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (threadIdx.x == 0) TL(1);
   // Everything above touched only this CTA's shared memory / TMEM.  From here on global memory
   // written by the previous kernel of the stream is read: wait for it (no-op without PDL), then let
-  // the next kernel start its own prologue on SMs this grid leaves.
-  griddep_wait();
-  griddep_launch_dependents();
-  if (threadIdx.x == 0) TL(2);
+  // the next kernel start its own prologue on SMs this grid leaves.  The TMA producer thread waits
+  // inside its own loop (below): in inference kernels it first streams the W tiles of the first
+  // pipeline stages, which no kernel of the forward writes.
+  // No lane of the producer's warp may execute griddepcontrol.wait: the instruction stalls the
+  // whole warp, diverged lanes included (measured: the producer lane did not issue anything until
+  // the wait of its sibling lanes had returned).  The MMA thread tells the producer through an
+  // mbarrier that the wait has returned -- the prerequisite grids' writes are visible to the whole
+  // grid from then on.
+  if (warp != 0) {
+    griddep_wait();
+    griddep_launch_dependents();
+  }
+  if (threadIdx.x == 32) {
+    mbar_arrive(dep_bar);
+    TL(2);
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      // Weights ahead of the dependency wait: the packed weights are written at plan build / by the
+      // optimiser step, always at least one full kernel boundary (the input pack) before any conv
+      // kernel of a forward, so they are safe to read while the previous layer is still running.
+      // Besides hiding the cold-HBM latency of the first W tiles this runs the loop body once
+      // before the wait: the instruction fetches of the first iterations (measured: 1.5-3 k cycles
+      // of instruction-cache misses between the wait and the first load) move off the critical path.
+      // Training kernels keep the plain order (their weight packs change every step).
+      constexpr bool kEarlyW = !TRAIN;
+      if (!kEarlyW) mbar_wait(dep_bar, 0);
       if (WRES) {
         // every (plane, tap, k-block) tile of this CTA's N block, once
         const int n_blk = blockIdx.x % p.n_tiles;
@@ -333,52 +355,74 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       slab * p.n_pad + n_blk * BLOCK_N);
         }
       }
-      for (int w = worker; w < total_tiles; w += num_workers) {
+      // mode 0: W only (before the wait), 1: the A tiles of those same stages, 2: steady state
+      const int n_pre = (kEarlyW && !WRES) ? (k_iters < kStages ? k_iters : kStages) : 0;
+      int mode = n_pre > 0 ? 0 : 2;
+      if (kEarlyW && mode == 2) mbar_wait(dep_bar, 0);
+      int w = worker;
+      if (w < total_tiles) {
         int n_blk, sample, row0;
         tile_coords(p, tile_of(w), n_blk, sample, row0);
-        for (int pair = 0; pair < p.pairs; ++pair) {
+        uint32_t stage = 0, phase = 0;
+        int it = 0, pair = 0, tap = 0, kb = 0;
+        for (;;) {
           const int a_plane = (pair == 1) ? 1 : 0;
           const int w_plane = (pair == 2) ? 1 : 0;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int a_row = row0 + tap * p.tap_row_step;
-            const int a_col0 = tap * p.tap_col_step;
-            // pairs: this CTA streams the W rows of its half of the N block
-            const int w_row = (w_plane * p.taps + tap) * p.n_pad + n_blk * BLOCK_N +
-                              (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
-            for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-              mbar_wait(empty_bar + stage * 8, phase ^ 1);
-              if (PAIR) {
-                // both CTAs' tiles are credited to the leader's barrier (the MMA issuer waits there)
-                const uint32_t lbar = leader_cta_addr(full_bar + stage * 8);
+          const uint32_t fb = full_bar + stage * 8;
+          // pairs: both CTAs' tiles are credited to the leader's barrier (the MMA issuer waits there)
+          const uint32_t lbar = PAIR ? leader_cta_addr(fb) : fb;
+          if (mode != 1) {
+            mbar_wait(empty_bar + stage * 8, phase ^ 1);
+            if (PAIR) {
+              if (is_leader) mbar_expect_tx(fb, 2 * Cfg::kStageBytes);
+            } else {
+              mbar_expect_tx(fb, Cfg::kStageBytes);
+            }
+            if (!WRES) {
+              // pairs: this CTA streams the W rows of its half of the N block
+              const int w_row = (w_plane * p.taps + tap) * p.n_pad + n_blk * BLOCK_N +
+                                (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
+              if (PAIR) tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
+              else tma_load_2d(&tmap_w, fb, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
 #ifdef VP3D_TIMELINE
-                const bool skip_w = (p.exp & 1) && (kb & 1), skip_a = (p.exp & 2) && (kb & 1);
-                if (is_leader)
-                  mbar_expect_tx(full_bar + stage * 8, 2 * ((skip_a ? 0u : Cfg::kABytes) +
-                                                            (skip_w ? 0u : Cfg::kBBytes)));
-                if (!skip_a)
-                  tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes,
-                                   a_col0 + kb * kBlockK, a_row, sample, a_plane);
-                if (!skip_w)
-                  tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
-#else
-                if (is_leader) mbar_expect_tx(full_bar + stage * 8, 2 * Cfg::kStageBytes);
-                tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes,
-                                 a_col0 + kb * kBlockK, a_row, sample, a_plane);
-                tma_load_2d_pair(&tmap_w, lbar, smem_b + stage * Cfg::kBBytes, kb * kBlockK, w_row);
-#endif
-              } else {
-                mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
-                tma_load_4d(&tmap_a, full_bar + stage * 8, smem_a + stage * Cfg::kABytes,
-                            a_col0 + kb * kBlockK, a_row, sample, a_plane);
-                if (!WRES)
-                  tma_load_2d(&tmap_w, full_bar + stage * 8, smem_b + stage * Cfg::kBBytes,
-                              kb * kBlockK, w_row);
-              }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-#ifdef VP3D_TIMELINE
-              if (w == worker && pair == 0 && tap == 0 && kb == 0) TL(3);
+              if (mode == 0 && it == 0) TL(23);
 #endif
             }
+          }
+          if (mode != 0) {
+            const int a_row = row0 + tap * p.tap_row_step;
+            const int a_col = tap * p.tap_col_step + kb * kBlockK;
+            if (PAIR) tma_load_4d_pair(&tmap_a, lbar, smem_a + stage * Cfg::kABytes, a_col, a_row, sample, a_plane);
+            else tma_load_4d(&tmap_a, fb, smem_a + stage * Cfg::kABytes, a_col, a_row, sample, a_plane);
+#ifdef VP3D_TIMELINE
+            if (w == worker && it == 0) TL(3);
+#endif
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          ++it;
+          if (++kb == p.kblocks_per_tap) {
+            kb = 0;
+            if (++tap == p.taps) { tap = 0; ++pair; }
+          }
+          if (mode == 0 && it == n_pre) {
+#ifdef VP3D_TIMELINE
+            TL(22);
+#endif
+            mbar_wait(dep_bar, 0);
+#ifdef VP3D_TIMELINE
+            TL(21);
+#endif
+            mode = 1;   // rewind: the A tiles of the stages just primed
+            it = 0; pair = 0; tap = 0; kb = 0;
+            stage = 0; phase = 0;
+          } else if (mode == 1 && it == n_pre) {
+            mode = 2;
+          }
+          if (it == k_iters) {
+            w += num_workers;
+            if (w >= total_tiles) break;
+            tile_coords(p, tile_of(w), n_blk, sample, row0);
+            it = 0; pair = 0; tap = 0; kb = 0;
           }
         }
       }
@@ -1121,10 +1165,6 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_
   ConvGemmArgs args = args_in;
   args.timeline = (g_timeline && g_timeline_next < g_timeline_max)
                       ? g_timeline + (size_t)(g_timeline_next++) * 128 : nullptr;
-  {
-    const char* e = getenv("VP3D_EXP");
-    args.exp = e ? atoi(e) : 0;
-  }
 #else
   const ConvGemmArgs& args = args_in;
 #endif

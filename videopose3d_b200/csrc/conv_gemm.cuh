@@ -98,10 +98,8 @@ struct ConvGemmArgs {
   // [lo_row_begin, lo_row_end) (flat tiling; the rows a later residual add / split-bf16 GEMM reads)
   int lo_row_begin, lo_row_end;
 #ifdef VP3D_TIMELINE
-  // debug build (`make dbg`): per-launch time stamps of the first and the last CTA, and traffic
-  // experiments (exp bit 0 / 1: skip the W / A loads of odd k-blocks -- wrong results, timing only)
+  // debug build (`make dbg`): per-launch time stamps of the first and the last CTA
   unsigned long long* timeline;   // [2 CTAs][32 events][globaltimer ns, clock64] or null
-  int exp;
 #endif
 };
 #ifdef VP3D_TIMELINE
