@@ -202,6 +202,17 @@ int run_wgrad(const vp3d_plan* p, const WgradCall& c, float* partial, size_t par
   const long long total_kb = (long long)a.kchunks * a.samples;
   int splits = (2 * num_sms() + items - 1) / items;
   if (splits > 8) splits = 8;
+  if (wgrad_gemm_uses_pair(a, block_n, num_sms())) {
+    // CTA pairs: pick the split count that minimises (waves of pair tiles) x (k-chunks per split);
+    // ties go to fewer splits (less partial traffic for wgrad_reduce)
+    const long long units = (long long)c.taps * (a.m_tiles / 2) * a.n_tiles, workers = num_sms() / 2;
+    double best = 0.0;
+    for (int sp = 1; sp <= 8; ++sp) {
+      const long long waves = (units * sp + workers - 1) / workers;
+      const double cost = (double)waves * (double)((total_kb + sp - 1) / sp) * (1.0 + 0.02 * sp);
+      if (best == 0.0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
   if (splits > total_kb) splits = (int)total_kb;
   if (splits < 1) splits = 1;
   while ((size_t)splits * c.taps * a.m_pad * a.n_pad * 4 > partial_bytes && splits > 1) --splits;

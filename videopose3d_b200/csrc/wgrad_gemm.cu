@@ -5,6 +5,9 @@
 // channels] boxes: channels (the M / N index of the GEMM) are contiguous, so the shared-memory
 // descriptors are MN-major SWIZZLE_128B (LBO = distance between 64-channel groups = one 8 KiB box,
 // SBO = 1024 B between 8-row groups) and a K = 16 step advances the start address by 16 rows.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ptx.cuh"
 #include "wgrad_gemm.cuh"
 
@@ -15,11 +18,17 @@ constexpr int kWM = 128;
 constexpr int kWK = 64;
 constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // 64 rows x 64 channels bf16
 
-template <int BLOCK_N>
+// PAIR (BLOCK_N = 256, even number of C_out tiles): clusters of two CTAs compute a 256 x 256 tile
+// of one (tap, split) together with one tcgen05.mma.cta_group::2 stream issued by the cluster's
+// rank-0 CTA; each CTA loads its own 128 dZ channels and HALF of the X channels (32 instead of
+// 48 KiB per k-chunk), which is what the shared-memory-port-bound single-CTA tiles were missing
+// (768 -> 512 port cycles per chunk) and deepens the operand pipeline from 4 to 6 stages.
+template <int BLOCK_N, bool PAIR = false>
 struct WCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static_assert(!PAIR || BLOCK_N == 256, "CTA pairs run 256-wide tiles");
+  static constexpr int kStages = PAIR ? 6 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr uint32_t kABytes = 2 * kBoxBytes;
-  static constexpr uint32_t kBBytes = (BLOCK_N / 64) * kBoxBytes;
+  static constexpr uint32_t kBBytes = ((PAIR ? BLOCK_N / 2 : BLOCK_N) / 64) * kBoxBytes;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
@@ -30,25 +39,27 @@ struct Item {
   int tap, m_blk, n_blk, split, kb_begin, kb_end;
 };
 
-__device__ __forceinline__ Item decode_item(const WgradArgs& p, int item) {
+// m_units: C_out tiles (single CTAs) or pairs of them (CTA pairs: this CTA takes tile 2*unit + rank)
+__device__ __forceinline__ Item decode_item(const WgradArgs& p, int item, int m_units, int m_mul,
+                                            int m_add) {
   Item it;
   it.split = item % p.splits;
   int r = item / p.splits;
   it.n_blk = r % p.n_tiles;
   r /= p.n_tiles;
-  it.m_blk = r % p.m_tiles;
-  it.tap = r / p.m_tiles;
+  it.m_blk = (r % m_units) * m_mul + m_add;
+  it.tap = r / m_units;
   const int total_kb = p.per_sample ? p.samples * p.kchunks : p.kchunks;
   it.kb_begin = (int)((long long)it.split * total_kb / p.splits);
   it.kb_end = (int)((long long)(it.split + 1) * total_kb / p.splits);
   return it;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__(256, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
                   const __grid_constant__ CUtensorMap tmap_x, const WgradArgs p) {
-  using Cfg = WCfg<BLOCK_N>;
+  using Cfg = WCfg<BLOCK_N, PAIR>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -68,7 +79,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = p.taps * p.m_tiles * p.n_tiles * p.splits;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = PAIR ? p.m_tiles / 2 : p.m_tiles;
+  const int m_mul = PAIR ? 2 : 1, m_add = (int)cta_rank;
+  const int total_items = p.taps * m_units * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_dz);
@@ -81,21 +98,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s * 8, 1);
-      mbar_init(tempty_bar + s * 8, 128);
+      mbar_init(tempty_bar + s * 8, PAIR ? 256 : 128);   // pairs: both CTAs' epilogues, on the leader's
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
+      for (int item = worker; item < total_items; item += num_workers) {
+        const Item it = decode_item(p, item, m_units, m_mul, m_add);
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           int sample = 0, krow = kb * kWK;
           if (p.per_sample) {
@@ -106,29 +127,47 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
             const int a_plane = (pair == 1) ? 1 : 0;
             const int b_plane = (pair == 2) ? 1 : 0;
             mbar_wait(empty_bar + stage * 8, phase ^ 1);
-            mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
             const uint32_t sa = smem_a + stage * Cfg::kABytes;
             const uint32_t sb = smem_b + stage * Cfg::kBBytes;
+            if (PAIR) {
+              // both CTAs' boxes are credited to the leader's barrier (the MMA issuer waits there);
+              // this CTA streams the X channels of its half of the N block
+              const uint32_t lbar = leader_cta_addr(full_bar + stage * 8);
+              if (is_leader) mbar_expect_tx(full_bar + stage * 8, 2 * Cfg::kStageBytes);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d(&tmap_dz, full_bar + stage * 8, sa + j * kBoxBytes,
-                          it.m_blk * kWM + j * 64, krow, sample, a_plane);
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d_pair(&tmap_dz, lbar, sa + j * kBoxBytes, it.m_blk * kWM + j * 64, krow,
+                                 sample, a_plane);
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_4d(&tmap_x, full_bar + stage * 8, sb + j * kBoxBytes,
-                          it.tap * p.tap_col_step + it.n_blk * BLOCK_N + j * 64,
-                          krow + it.tap * p.tap_row_step, sample, b_plane);
+              for (int j = 0; j < BLOCK_N / 128; ++j)
+                tma_load_4d_pair(&tmap_x, lbar, sb + j * kBoxBytes,
+                                 it.tap * p.tap_col_step + it.n_blk * BLOCK_N +
+                                     (int)cta_rank * (BLOCK_N / 2) + j * 64,
+                                 krow + it.tap * p.tap_row_step, sample, b_plane);
+            } else {
+              mbar_expect_tx(full_bar + stage * 8, Cfg::kStageBytes);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d(&tmap_dz, full_bar + stage * 8, sa + j * kBoxBytes,
+                            it.m_blk * kWM + j * 64, krow, sample, a_plane);
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_4d(&tmap_x, full_bar + stage * 8, sb + j * kBoxBytes,
+                            it.tap * p.tap_col_step + it.n_blk * BLOCK_N + j * 64,
+                            krow + it.tap * p.tap_row_step, sample, b_plane);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kWM, BLOCK_N, 1, 1);  // both operands MN-major
+    if (lane == 0 && is_leader) {
+      // both operands MN-major; pairs: one 256-row MMA over both CTAs
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kWM : kWM, BLOCK_N, 1, 1);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
+      for (int item = worker; item < total_items; item += num_workers) {
+        const Item it = decode_item(p, item, m_units, m_mul, m_add);
         const int iters = (it.kb_end - it.kb_begin) * p.pairs;
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1);
         tc_fence_after();
@@ -142,20 +181,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
           for (int k = 0; k < kWK / 16; ++k) {
             const uint64_t da = make_smem_desc_mn_sw128(sa + k * 2048, kBoxBytes, 1024);
             const uint64_t db = make_smem_desc_mn_sw128(sb + k * 2048, kBoxBytes, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (i | k) ? 1u : 0u);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (i | k) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, da, db, idesc, (i | k) ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage * 8);
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if (PAIR) umma_commit_pair(empty_bar + stage * 8);
+          else umma_commit(empty_bar + stage * 8);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + acc * 8);
+        if (PAIR) umma_commit_pair(tfull_bar + acc * 8);
+        else umma_commit(tfull_bar + acc * 8);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     const int ew = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+    const uint32_t tempty_addr = PAIR ? leader_cta_addr(tempty_bar) : tempty_bar;
+    for (int item = worker; item < total_items; item += num_workers) {
+      const Item it = decode_item(p, item, m_units, m_mul, m_add);
       const int co = it.m_blk * kWM + ew * 32 + lane;
       float* dst = p.partial +
                    (((long long)it.split * p.taps + it.tap) * p.m_pad + co) * p.n_pad +
@@ -175,24 +219,28 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
                               __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + acc * 8);
+      if (PAIR) mbar_arrive_cluster(tempty_addr + acc * 8); else mbar_arrive(tempty_addr + acc * 8);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  // pairs: neither CTA may leave (or free TMEM) while the other can still read its shared memory
+  // through the pair MMAs or signal its barriers
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tmap_x,
                               const WgradArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = WCfg<BLOCK_N>;
+  using Cfg = WCfg<BLOCK_N, PAIR>;
+  auto kernel = wgrad_gemm_kernel<BLOCK_N, PAIR>;
   // the dynamic shared memory opt-in is a per-device attribute
   static bool attr_set[64] = {};
   int dev = 0;
@@ -200,16 +248,32 @@ cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tma
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  const int total = a.taps * a.m_tiles * a.n_tiles * a.splits;
+  const int total = a.taps * (PAIR ? a.m_tiles / 2 : a.m_tiles) * a.n_tiles * a.splits;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < num_sms ? total : num_sms;
-  wgrad_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmap_dz, tmap_x, a);
-  return cudaGetLastError();
+  const int max_workers = PAIR ? num_sms / 2 : num_sms;
+  const int workers = total < max_workers ? total : max_workers;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(PAIR ? 2 * workers : workers, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int n_attr = 0;
+  if (PAIR) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  return cudaLaunchKernelEx(&cfg, kernel, tmap_dz, tmap_x, a);
 }
 
 // One thread per (co, ci): partial reads are coalesced along ci for every (split, tap); the taps of
@@ -237,11 +301,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 cudaError_t launch_wgrad_gemm(const CUtensorMap& tmap_dz, const CUtensorMap& tmap_x,
                               const WgradArgs& args, int block_n, int num_sms, cudaStream_t stream) {
   switch (block_n) {
-    case 256: return launch_wgrad_impl<256>(tmap_dz, tmap_x, args, num_sms, stream);
-    case 128: return launch_wgrad_impl<128>(tmap_dz, tmap_x, args, num_sms, stream);
-    case 64: return launch_wgrad_impl<64>(tmap_dz, tmap_x, args, num_sms, stream);
+    case 256:
+      if (wgrad_gemm_uses_pair(args, block_n, num_sms))
+        return launch_wgrad_impl<256, true>(tmap_dz, tmap_x, args, num_sms, stream);
+      return launch_wgrad_impl<256, false>(tmap_dz, tmap_x, args, num_sms, stream);
+    case 128: return launch_wgrad_impl<128, false>(tmap_dz, tmap_x, args, num_sms, stream);
+    case 64: return launch_wgrad_impl<64, false>(tmap_dz, tmap_x, args, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// CTA pairs: 256-wide tiles, an even number of C_out tiles, an even number of SMs (VP3D_PAIR=0 off)
+bool wgrad_gemm_uses_pair(const WgradArgs& args, int block_n, int num_sms) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VP3D_PAIR");
+    on = (e && e[0] == '0') ? 0 : 1;
+    const char* w = getenv("VP3D_PAIR_WGRAD");   // measurement knob: wgrad pairs alone
+    if (w && w[0] == '0') on = 0;
+  }
+  return on && block_n == 256 && !(args.m_tiles & 1) && !(num_sms & 1);
 }
 
 cudaError_t launch_wgrad_reduce(const float* partial, float* grad, int splits, int taps_p, int m_pad,

@@ -32,6 +32,10 @@ struct WgradArgs {
   float* partial;       // [splits][taps][m_pad][n_pad]
 };
 
+// Whether launch_wgrad_gemm runs this launch on CTA pairs (256 x 256 tiles over two SMs); the split
+// count is best chosen for num_sms / 2 workers then.
+bool wgrad_gemm_uses_pair(const WgradArgs& args, int block_n, int num_sms);
+
 cudaError_t launch_wgrad_gemm(const CUtensorMap& tmap_dz, const CUtensorMap& tmap_x,
                               const WgradArgs& args, int block_n, int num_sms, cudaStream_t stream);
 
