@@ -201,7 +201,8 @@ int run_wgrad(const vp3d_plan* p, const WgradCall& c, float* partial, size_t par
   const int items = c.taps * a.m_tiles * a.n_tiles;
   const long long total_kb = (long long)a.kchunks * a.samples;
   int splits = (2 * num_sms() + items - 1) / items;
-  if (splits > 8) splits = 8;
+  // (up to 16 row ranges: the expand conv's gradient has only C_out / 128 tiles to spread)
+  if (splits > 16) splits = 16;
   if (wgrad_gemm_uses_pair(a, block_n, num_sms())) {
     // CTA pairs: pick the split count that minimises (waves of pair tiles) x (k-chunks per split);
     // ties go to fewer splits (less partial traffic for wgrad_reduce)
