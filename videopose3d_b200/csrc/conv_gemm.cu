@@ -1024,6 +1024,7 @@ static bool pdl_enabled() {
   return g_pdl != 0;
 }
 void conv_gemm_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+bool conv_gemm_pdl_enabled() { return pdl_enabled(); }
 
 // CTA pairs (cta_group::2) for the 256-wide streamed-W launches: VP3D_PAIR=0 turns them off.
 static bool pair_enabled() {

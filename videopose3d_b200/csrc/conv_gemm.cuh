@@ -119,6 +119,7 @@ bool conv_gemm_uses_pair(const ConvGemmArgs& args, int block_n, int num_sms);
 bool conv_gemm_uses_wres(const ConvGemmArgs& args, int block_n, int num_sms);
 bool conv_gemm_pairs_enabled();   // VP3D_PAIR != 0
 void conv_gemm_set_pdl(int on);   // programmatic dependent launch of the GEMM kernels (default on)
+bool conv_gemm_pdl_enabled();     // (also honoured by the small kernels between the GEMMs, launch.cuh)
 cudaError_t launch_conv_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w,
                              const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const CUtensorMap& tmap_z, const ConvGemmArgs& args, int block_n,

@@ -137,6 +137,8 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* out, int planes, in
   long long blocks = items;
   if (blocks > 148 * 8) blocks = 148 * 8;
   const bool vec2 = (c_raw % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
+  // (a plain launch: the input pack is the first kernel of a forward and usually follows a copy or
+  // an event wait, where a programmatic edge buys nothing)
   if (vec2)
     pack_input_kernel<true><<<(int)blocks, 256, 0, stream>>>(
         x, out, planes, N, T, c_raw, rows, group, frame_step, k_pad, plane_stride, pp, f16);

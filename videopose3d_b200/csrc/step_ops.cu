@@ -118,28 +118,42 @@ adam_pack_kernel(const __grid_constant__ PackBatch batch, const AdamHyper h) {
   const long long fwd_plane = (long long)q.taps * q.fwd_n_pad * q.fwd_k_pad;
   const long long tr_plane = (long long)q.taps * q.tr_n_pad * q.tr_k_pad;
   for (int tap = 0; tap < q.taps; ++tap) {
+    // all five streams of this thread's four elements are loaded before the first update: the
+    // stores of the update may alias the loads as far as the compiler knows, and one element at a
+    // time (20 bytes in flight per thread) left the pass latency-bound at half the HBM rate
+    float pv[4], gv[4], mv[4], vv[4], xv[4];
+    bool live[4];
 #pragma unroll
-    for (int j = ty; j < 32; j += 8) {
+    for (int u = 0; u < 4; ++u) {
+      const int co = co0 + ty + 8 * u, ci = ci0 + tx;
+      live[u] = co < q.c_out && ci < q.c_in;
+      const long long k = live[u] ? ((long long)co * q.c_in + ci) * q.taps + tap : 0;
+      pv[u] = live[u] ? q.t.param[k] : 0.0f;
+      gv[u] = live[u] ? q.t.grad[k] : 0.0f;
+      mv[u] = live[u] ? q.t.exp_avg[k] : 0.0f;
+      vv[u] = live[u] ? q.t.exp_avg_sq[k] : 0.0f;
+      xv[u] = (live[u] && amsgrad) ? q.t.max_exp_avg_sq[k] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = ty + 8 * u;
       const int co = co0 + j, ci = ci0 + tx;
-      float pv = 0.0f;
-      if (co < q.c_out && ci < q.c_in) {
+      if (live[u]) {
         const long long k = ((long long)co * q.c_in + ci) * q.taps + tap;
-        pv = q.t.param[k];
-        float m = q.t.exp_avg[k], v = q.t.exp_avg_sq[k];
-        float x = amsgrad ? q.t.max_exp_avg_sq[k] : 0.0f;
-        adam_update(pv, q.t.grad[k], m, v, x, amsgrad, h);
-        q.t.param[k] = pv;
-        q.t.exp_avg[k] = m;
-        q.t.exp_avg_sq[k] = v;
-        if (amsgrad) q.t.max_exp_avg_sq[k] = x;
+        adam_update(pv[u], gv[u], mv[u], vv[u], xv[u], amsgrad, h);
+        q.t.param[k] = pv[u];
+        q.t.exp_avg[k] = mv[u];
+        q.t.exp_avg_sq[k] = vv[u];
+        if (amsgrad) q.t.max_exp_avg_sq[k] = xv[u];
         if (q.fwd) {
           const long long o = ((long long)tap * q.fwd_n_pad + co) * q.fwd_k_pad + ci;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(pv);
+          const __nv_bfloat16 hi = __float2bfloat16_rn(pv[u]);
           q.fwd[o] = hi;
-          if (batch.planes == 2) q.fwd[fwd_plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+          if (batch.planes == 2)
+            q.fwd[fwd_plane + o] = __float2bfloat16_rn(pv[u] - __bfloat162float(hi));
         }
       }
-      sm[j][tx] = pv;
+      sm[j][tx] = pv[u];
     }
     __syncthreads();
     if (q.tr) {

@@ -1,5 +1,7 @@
 #include "train_ops.cuh"
 
+#include "launch.cuh"
+
 namespace vp3d {
 
 namespace {
@@ -121,6 +123,7 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int slabs, SlabGeom geo
                          float* __restrict__ shift, float* __restrict__ mean_out,
                          float* __restrict__ invstd, float* __restrict__ scratch,
                          unsigned* __restrict__ counter) {
+  pdl_entry();
   __shared__ float sm[8][3][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
@@ -219,6 +222,7 @@ ordered_col_sums_kernel(const float* __restrict__ part, int n_part, int nstat, i
                         int folds, const float* __restrict__ mul0, const float* __restrict__ mul1,
                         float* __restrict__ out0, float* __restrict__ out1,
                         float* __restrict__ scratch, unsigned* __restrict__ counter) {
+  pdl_entry();
   __shared__ float sm[8][2][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
@@ -305,6 +309,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, long long z_plane,
                 const float* __restrict__ scale, const float* __restrict__ shift, DropoutCfg drop,
                 const __nv_bfloat16* __restrict__ res, long long res_plane, RowMap map,
                 RowTiling tl) {
+  pdl_entry();
   const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
   const int c0 = (blockIdx.x * tl.G + cg) * 8;
   const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
@@ -400,6 +405,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
                      const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, DropoutCfg drop, float* __restrict__ sums,
                      RowTiling tl) {
+  pdl_entry();
   __shared__ float sm[2][2048];
   const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
   const int c0 = (blockIdx.x * tl.G + cg) * 8;
@@ -450,6 +456,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     DropoutCfg drop, const float* __restrict__ sums, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int c_real, RowTiling tl) {
+  pdl_entry();
   const int cg = threadIdx.x % tl.G, rl = threadIdx.x / tl.G, lanes = 256 / tl.G;
   const int c0 = (blockIdx.x * tl.G + cg) * 8;
   const long long r_begin = (long long)blockIdx.y * tl.rows_per_block;
@@ -518,6 +525,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, long long g_plane,
 
 __global__ void col_sum_f32_kernel(const float* __restrict__ x, long long rows, int c,
                                    float* __restrict__ out) {
+  pdl_entry();
   // one warp per 32-row chunk; lanes stride the channels
   const long long r0 = (long long)blockIdx.x * 64;
   for (int col = threadIdx.x; col < c; col += blockDim.x) {
@@ -608,10 +616,10 @@ cudaError_t launch_bn_stats_finalize(const float* part, int slabs, int dilated, 
   if (c > kReduceMaxChannels) return cudaErrorInvalidValue;
   SlabGeom g = {dilated, out_rows, tiles_per_sample};
   const dim3 grid((c + 31) / 32, pick_splits(slabs));
-  bn_stats_finalize_kernel<<<grid, 256, 0, stream>>>(part, slabs, g, c, c_real, gamma, beta, running_mean,
+  const cudaError_t le = launch_pdl(bn_stats_finalize_kernel, grid, dim3(256), 0, stream, part, slabs, g, c, c_real, gamma, beta, running_mean,
                                                      running_var, momentum, eps, scale, shift, mean,
                                                      invstd, scratch, counter);
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_ordered_col_sums(const float* part, int n_part, int nstat, int ld, int c,
@@ -620,9 +628,9 @@ cudaError_t launch_ordered_col_sums(const float* part, int n_part, int nstat, in
                                     cudaStream_t stream) {
   if (c > kReduceMaxChannels || nstat < 1 || nstat > 2) return cudaErrorInvalidValue;
   const dim3 grid((c + 31) / 32, pick_splits(n_part));
-  ordered_col_sums_kernel<<<grid, 256, 0, stream>>>(part, n_part, nstat, ld, c, folds, mul0, mul1,
+  const cudaError_t le = launch_pdl(ordered_col_sums_kernel, grid, dim3(256), 0, stream, part, n_part, nstat, ld, c, folds, mul0, mul1,
                                                     out0, out1, scratch, counter);
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bfloat16* x,
@@ -632,9 +640,9 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* z, long long z_plane, __nv_bflo
   if (rows <= 0) return cudaSuccess;
   dim3 grid;
   const RowTiling tl = row_tiling(rows, c, grid);
-  bn_apply_kernel<<<grid, 256, 0, stream>>>(z, z_plane, x, x_plane, planes, rows, c, scale, shift,
+  const cudaError_t le = launch_pdl(bn_apply_kernel, grid, dim3(256), 0, stream, z, z_plane, x, x_plane, planes, rows, c, scale, shift,
                                             drop, res, res_plane, map, tl);
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, const __nv_bfloat16* z,
@@ -648,9 +656,9 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* g, long long g_plane, cons
   // >= 32 rows per block: the per-block partials then fit the slab-partial buffer (rows / 32 slabs)
   const RowTiling tl = row_tiling(rows, c, grid, 32);
   if ((size_t)grid.y * 2 * c > partial_floats) return cudaErrorInvalidValue;
-  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, planes, rows, c, scale,
+  const cudaError_t le = launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, stream, g, g_plane, z, z_plane, planes, rows, c, scale,
                                                  shift, mean, invstd, drop, partials, tl);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_ordered_col_sums(partials, (int)grid.y, 2, c, c, 1, nullptr, invstd, sums, sums + c,
                                  scratch, counter, stream);
@@ -665,10 +673,10 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* g, long long g_plane, const
   if (rows <= 0) return cudaSuccess;
   dim3 grid;
   const RowTiling tl = row_tiling(rows, c, grid);
-  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(g, g_plane, z, z_plane, dz, dz_plane, planes, rows,
+  const cudaError_t le = launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, stream, g, g_plane, z, z_plane, dz, dz_plane, planes, rows,
                                                 c, scale, shift, mean, invstd, drop, sums, dgamma,
                                                 dbeta, c_real, tl);
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* partials,
@@ -677,8 +685,8 @@ cudaError_t launch_col_sum_f32(const float* x, long long rows, int c, float* par
   if (rows <= 0) return cudaSuccess;
   const unsigned chunks = (unsigned)((rows + 63) / 64);
   if ((size_t)chunks * c > partial_floats) return cudaErrorInvalidValue;
-  col_sum_f32_kernel<<<chunks, 64, 0, stream>>>(x, rows, c, partials);
-  cudaError_t e = cudaGetLastError();
+  const cudaError_t le = launch_pdl(col_sum_f32_kernel, dim3(chunks), dim3(64), 0, stream, x, rows, c, partials);
+  cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_ordered_col_sums(partials, (int)chunks, 1, c, c, 1, nullptr, nullptr, out, nullptr,
                                  scratch, counter, stream);

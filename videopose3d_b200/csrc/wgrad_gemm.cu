@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "launch.cuh"
 #include "ptx.cuh"
 #include "wgrad_gemm.cuh"
 
@@ -111,6 +112,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dz,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // (set-up above overlaps the predecessor's tail under programmatic dependent launch)
+  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -262,8 +265,13 @@ cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tma
   cfg.blockDim = dim3(256, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int n_attr = 0;
+  if (conv_gemm_pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   if (PAIR) {
     attr[n_attr].id = cudaLaunchAttributeClusterDimension;
     attr[n_attr].val.clusterDim.x = 2;
@@ -276,24 +284,34 @@ cudaError_t launch_wgrad_impl(const CUtensorMap& tmap_dz, const CUtensorMap& tma
   return cudaLaunchKernelEx(&cfg, kernel, tmap_dz, tmap_x, a);
 }
 
-// One thread per (co, ci): partial reads are coalesced along ci for every (split, tap); the taps of
-// one (co, ci) are written as one contiguous run of the (c_out, c_in, taps) gradient layout.
+// One thread per gradient element (co, ci, tap) in the (c_out, c_in, taps) order of
+// Conv1d.weight.grad: the writes are fully coalesced and the split partials of an element are the
+// only serial chain (summed left to right: deterministic).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                     int splits, int taps_p, int m_pad, int n_pad, int c_out, int c_in,
                                     int taps_out, int merged) {
-  const long long total = (long long)c_out * c_in;
+  pdl_entry();
+  const long long total = (long long)c_out * c_in * taps_out;
   const long long split_stride = (long long)taps_p * m_pad * n_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % taps_out);
+    const long long i = e / taps_out;
     const int ci = (int)(i % c_in);
     const int co = (int)(i / c_in);
-    for (int tap = 0; tap < taps_out; ++tap) {
-      const long long src = merged ? ((long long)co * n_pad + tap * c_in + ci)
-                                   : (((long long)tap * m_pad + co) * n_pad + ci);
-      float s = 0.0f;
-      for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + sp * split_stride + src);
-      grad[i * taps_out + tap] = s;
+    const long long src = merged ? ((long long)co * n_pad + tap * c_in + ci)
+                                 : (((long long)tap * m_pad + co) * n_pad + ci);
+    float s = 0.0f;
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {   // four loads in flight, same summation order
+      const float a = __ldg(partial + (sp + 0) * split_stride + src);
+      const float b = __ldg(partial + (sp + 1) * split_stride + src);
+      const float c = __ldg(partial + (sp + 2) * split_stride + src);
+      const float d = __ldg(partial + (sp + 3) * split_stride + src);
+      s += a; s += b; s += c; s += d;
     }
+    for (; sp < splits; ++sp) s += __ldg(partial + sp * split_stride + src);
+    grad[e] = s;
   }
 }
 }  // namespace
@@ -326,13 +344,14 @@ bool wgrad_gemm_uses_pair(const WgradArgs& args, int block_n, int num_sms) {
 cudaError_t launch_wgrad_reduce(const float* partial, float* grad, int splits, int taps_p, int m_pad,
                                 int n_pad, int c_out, int c_in, int taps_out, int merged,
                                 cudaStream_t stream) {
-  const long long total = (long long)c_out * c_in;
+  const long long total = (long long)c_out * c_in * taps_out;
   if (total <= 0) return cudaSuccess;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, grad, splits, taps_p, m_pad, n_pad,
-                                                       c_out, c_in, taps_out, merged);
-  return cudaGetLastError();
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  const cudaError_t le = launch_pdl(wgrad_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream,
+                                    partial, grad, splits, taps_p, m_pad, n_pad, c_out, c_in, taps_out,
+                                    merged);
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace vp3d
