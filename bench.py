@@ -612,9 +612,16 @@ def run_ours(args, rank, local_rank, world):
         # (b) the same per-step work through the two-slot pipelined calls: the PCIe copy of step
         # i+1 overlaps the kernels of step i; every step still moves its own input and output
         yhs = [yh, torch.empty_like(yh).pin_memory()]
-        for i in range(4):
-            model.forward_host_submit(xh[i % 2], yhs[i % 2], i % 2)
-            model.forward_host_wait(i % 2)
+        # untimed warm-up of the pipelined path itself: the device-timed loop above moved nothing
+        # over PCIe for milliseconds, and the first copies after such a pause ran at half rate on
+        # some boxes (link power state) -- 1.2 instead of 0.65 ms/step over a 30-step window
+        for i in range(max(32, args.warmup)):
+            s = i & 1
+            if i >= 2:
+                model.forward_host_wait(s)
+            model.forward_host_submit(xh[s], yhs[s], s)
+        model.forward_host_wait(0)
+        model.forward_host_wait(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
