@@ -440,7 +440,9 @@ def measure_train(dev, rank, world, steps, warmup, n_seq, compress=None):
         local_ms, local_wall_ms, _ = timed(steps)
         reducer.attach(model)
         out["local_step_ms_no_collective"] = local_ms
-    for _ in range(max(3, warmup)):
+    # (NCCL sets its channels up lazily: the first collectives of a process are several times
+    # slower, and a 3-step warm-up left them inside the timed window on some boxes)
+    for _ in range(max(12 if world > 1 else 3, warmup)):
         step()
     launches_bwd = model.last_launch_count()
     gpu_ms, wall_ms, last_loss = timed(steps)

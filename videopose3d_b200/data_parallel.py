@@ -68,13 +68,15 @@ class GradientReducer:
     def attach(self, module):
         """Route `module`'s training backward through this reducer; returns the reducer.
 
-        With overlap on a CUDA device the GEMM kernels' programmatic dependent launch is switched
-        off for the process: kernels that hand every SM over without a gap leave the NCCL kernels
-        of the side stream nowhere to run (measured on 2 x B200: 2.76 ms / step with it off; with
-        it on the step is as fast only while the launch queue stays full and collapses to tens of
-        ms when the host synchronises every step, as run.py's `loss.item()` does)."""
+        With more than one rank on CUDA devices the kernels' programmatic dependent launch is
+        switched off for the process: kernels that hand every SM over without a gap leave the NCCL
+        kernels nowhere to run (measured on 2 x B200: 2.76 ms / step with it off; with it on the
+        step is as fast only in one of the two regimes -- launch queue full or a host sync every
+        step, as run.py's `loss.item()` does -- and collapses to tens of ms in the other; since
+        the small kernels between the GEMMs also chain programmatically this holds without
+        overlap too)."""
         object.__setattr__(module, "_grad_reducer", self)
-        if self.overlap and self.world > 1 and torch.cuda.is_available():
+        if self.world > 1 and torch.cuda.is_available():
             from . import _capi
             _capi.check(_capi.load().vp3d_set_pdl(0), "vp3d_set_pdl")
         return self
