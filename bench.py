@@ -398,7 +398,8 @@ def measure_train(dev, rank, world, steps, warmup, n_seq, compress=None):
                                         channels=C).to(dev).train()
     opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
     overlap = bool(int(os.environ.get("VP3D_BENCH_DP_OVERLAP", "1")))
-    reducer = GradientReducer(overlap=overlap, compress=compress) if world > 1 else None
+    reserve = int(os.environ.get("VP3D_BENCH_DP_RESERVE_SMS", "0"))
+    reducer = GradientReducer(overlap=overlap, compress=compress, reserve_sms=reserve) if world > 1 else None
 
     def step():
         _, y3, x2 = next(it)
@@ -542,7 +543,14 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL kernels on a high-priority stream: the gradient all-reduce overlaps persistent
+        # one-CTA-per-SM GEMM grids; at default priority its CTAs queue behind every pending compute
+        # CTA, the two ranks enter the collective far apart and spin on each other for milliseconds
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=dev)
 
     # random-init weights of the named architecture (no datasets / checkpoints offline)
     sd = orc.make_state_dict(J, F, J, ARC, C, seed=0)

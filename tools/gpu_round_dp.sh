@@ -19,5 +19,5 @@ except Exception as e: print('${name} ERR',e)
 "
 }
 run default VP3D_DUMMY=1
-run no_overlap VP3D_BENCH_DP_OVERLAP=0
-run default_again VP3D_DUMMY=1
+run default_2 VP3D_DUMMY=1
+run default_3 VP3D_DUMMY=1

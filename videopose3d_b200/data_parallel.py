@@ -34,12 +34,16 @@ class GradientReducer:
     all-reduce it stage by stage (overlapped on CUDA); `reduce_flat` is the device-agnostic core and
     is what the CPU (gloo) tests exercise."""
 
-    def __init__(self, process_group=None, overlap=True, compress=None):
+    def __init__(self, process_group=None, overlap=True, compress=None, reserve_sms=0):
         """compress: None (fp32 all-reduce) or "bf16" (each slice is rounded to bf16 for the wire
         and widened back: half the NVLink bytes; the rounding error, 2^-9 relative per rank
-        contribution, is below the bf16 training noise floor)."""
+        contribution, is below the bf16 training noise floor).
+        reserve_sms: with overlap, cap the persistent GEMM grids at (SM count - reserve_sms) so
+        that the NCCL kernels of the side stream always find free SMs (pair it with
+        NCCL_MAX_CTAS <= reserve_sms in the environment)."""
         if compress not in (None, "bf16"):
             raise ValueError("compress must be None or 'bf16'")
+        self.reserve_sms = int(reserve_sms)
         self.group = process_group
         self.overlap = overlap
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -79,6 +83,11 @@ class GradientReducer:
         if self.world > 1 and torch.cuda.is_available():
             from . import _capi
             _capi.check(_capi.load().vp3d_set_pdl(0), "vp3d_set_pdl")
+            if self.overlap and self.reserve_sms > 0:
+                sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                limit = (sms - self.reserve_sms) & ~1   # even: the GEMMs run on CTA pairs
+                if limit >= 2:
+                    _capi.check(_capi.load().vp3d_set_sm_limit(limit), "vp3d_set_sm_limit")
         return self
 
     def set_step_rows(self, local_rows, global_rows):
@@ -120,7 +129,8 @@ class GradientReducer:
             return
         cur = torch.cuda.current_stream(flat.device)
         if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream(device=flat.device)
+            # (high priority: the collective's kernels must not queue behind the compute grids)
+            self.comm_stream = torch.cuda.Stream(device=flat.device, priority=-1)
         ev = torch.cuda.Event()
         ev.record(cur)
         with torch.cuda.stream(self.comm_stream):
