@@ -37,3 +37,15 @@ def test_single_stage_needs_the_release_wait():
 def test_single_stage_is_still_not_safe_for_unsynchronised_sibling_threads():
     # documented limitation: never launch with one auxiliary stage (run_conv's tile-width rule)
     assert _first_error(1, 2, "main", runs=400, threads_per_group=2) is not None
+
+
+@pytest.mark.parametrize("slots", [2, 4])
+@pytest.mark.parametrize("blocks_per_tile", [1, 2, 4])
+def test_inplace_residual_epilogue_is_hazard_and_deadlock_free(slots, blocks_per_tile):
+    # the lean inference epilogue (LEAN && RES): result written over the consumed residual tile,
+    # slot handed back by each thread once its own bulk store has read it
+    rng = random.Random(7)
+    for _ in range(150):
+        sim.simulate_inplace(slots, blocks_per_tile, rng.randint(3, 9), rng, threads_per_group=2)
+    for _ in range(50):
+        sim.simulate_inplace(slots, blocks_per_tile, rng.randint(3, 9), rng, threads_per_group=4)

@@ -12,6 +12,9 @@ producer never overwrites a stage still being read, and that nobody deadlocks.
 
     python tools/sim_epilogue_protocol.py [--runs 2000]
 
+`simulate_inplace` models the lean inference epilogue that stages its result in the residual
+landing slot (4 slots, handed back per thread after its bulk store has read them).
+
 Variants: "main" = the shipped protocol (a consumer first waits for the RELEASE of the stage's
 previous use, then for its fill); "no_prewait" = the earlier, broken one (fill wait only).
 
@@ -134,6 +137,102 @@ def simulate(stages, blocks_per_tile, tiles, variant, rng, threads_per_group=2):
     return steps
 
 
+def simulate_inplace(stages, blocks_per_tile, tiles, rng, threads_per_group=2):
+    """The lean inference epilogue with a residual (conv_gemm.cu, LEAN && RES): store block a uses
+    landing slot a % stages -- with an even number of slots always the same group's --, every
+    thread writes its result over the residual bytes it has consumed, issues its own bulk store
+    from the slot, and hands the slot back (one arrival per thread) right before it waits for the
+    tile of its NEXT block, once that store has finished reading.  Checks: the producer never
+    refills a slot that is being read by a thread or by a store in flight, every consume finds the
+    expected tile, nobody deadlocks."""
+    assert stages % 2 == 0, "a slot must always belong to the same epilogue group"
+    n_blocks = tiles * blocks_per_tile
+    rfull = [MBar(1) for _ in range(stages)]
+    rempty = [MBar(threads_per_group) for _ in range(stages)]
+    tfull = [MBar(1) for _ in range(2)]
+    tempty = [MBar(2 * threads_per_group) for _ in range(2)]
+    slot = [None] * stages
+    readers = [0] * stages          # threads between their first read and their last write
+    storing = [0] * stages          # bulk stores still reading the slot
+
+    def producer():
+        for a in range(n_blocks):
+            rs, phase = a % stages, (a // stages) & 1
+            while not rempty[rs].done(phase ^ 1):
+                yield
+            if readers[rs] or storing[rs]:
+                raise ProtocolError(f"fill of block {a} overwrites slot {rs} while it is in use")
+            slot[rs] = a
+            yield
+            rfull[rs].arrive()
+            yield
+
+    def mma():
+        for t in range(tiles):
+            acc, phase = t & 1, (t >> 1) & 1
+            while not tempty[acc].done(phase ^ 1):
+                yield
+            yield
+            tfull[acc].arrive()
+
+    def consumer(group):
+        held = None                  # slot this thread's last bulk store was issued from
+        for t in range(tiles):
+            acc, phase = t & 1, (t >> 1) & 1
+            while not tfull[acc].done(phase):
+                yield
+            for sb in range(blocks_per_tile):
+                a = t * blocks_per_tile + sb
+                if (a & 1) != group:
+                    continue
+                rs, use = a % stages, a // stages
+                if held is not None:
+                    for _ in range(rng.randint(0, 3)):   # cp.async.bulk.wait_group.read
+                        yield
+                    storing[held] -= 1
+                    rempty[held].arrive()
+                held = rs
+                while not rfull[rs].done(use & 1):
+                    yield
+                if slot[rs] != a:
+                    raise ProtocolError(f"group {group} consumed slot {rs} holding block {slot[rs]} "
+                                        f"instead of {a}")
+                readers[rs] += 1
+                yield                # residual read, math, in-place write
+                if slot[rs] != a:
+                    raise ProtocolError(f"slot {rs} changed under the reader of block {a}")
+                readers[rs] -= 1
+                storing[rs] += 1     # the bulk store reads the slot from now on
+                yield
+            tempty[acc].arrive()
+            yield
+        # (the last store of a thread is drained by cp.async.bulk.wait_group 0 at kernel end)
+
+    actors = [producer(), mma()]
+    for g in range(2):
+        actors += [consumer(g) for _ in range(threads_per_group)]
+    live = list(actors)
+    steps, idle = 0, 0
+    bars = rfull + rempty + tfull + tempty
+    while live:
+        a = rng.choice(live)
+        before = (tuple(b.phase for b in bars), tuple(b.pending for b in bars), tuple(slot),
+                  tuple(readers), tuple(storing))
+        try:
+            next(a)
+        except StopIteration:
+            live.remove(a)
+            idle = 0
+            continue
+        after = (tuple(b.phase for b in bars), tuple(b.pending for b in bars), tuple(slot),
+                 tuple(readers), tuple(storing))
+        idle = idle + 1 if before == after else 0
+        steps += 1
+        if idle > 400 * len(live):
+            raise ProtocolError("deadlock: no actor can make progress")
+    return steps
+
+
 def check(variant, runs, seed=0):
     """Returns {(stages, blocks_per_tile): first error or None}."""
     rng = random.Random(seed)
@@ -159,3 +258,15 @@ if __name__ == "__main__":
         print(variant)
         for key, err in check(variant, args.runs).items():
             print(f"  stages {key[0]} blocks/tile {key[1]}: {'ok' if err is None else err}")
+    print("inplace (lean residual epilogue)")
+    rng = random.Random(1)
+    for stages in (2, 4):
+        for bpt in (1, 2, 4):
+            err = None
+            for _ in range(args.runs):
+                try:
+                    simulate_inplace(stages, bpt, rng.randint(3, 9), rng)
+                except ProtocolError as e:
+                    err = str(e)
+                    break
+            print(f"  slots {stages} blocks/tile {bpt}: {'ok' if err is None else err}")
